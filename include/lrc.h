@@ -1,0 +1,177 @@
+/*
+ * lrc.h -- C ABI of the B200-native LiDAR ray-casting engine (liblrc.so, sm_100a).
+ *
+ * This is the drop-in boundary for the ONE hot path of the reference:
+ *     RaycastEngine*.lidar_intersect_mesh / rays_intersect_mesh, called once per waypoint from
+ *     S3DISSimulator.run_simulation            (reference s3dis_simulator.py:254-288, :261)
+ * The reference has no FFI of its own (pure Python over Open3D/Embree); every entry point below
+ * names the reference interface it replaces.  All citations are relative to the reference tree.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++/torch types cross the boundary.
+ *   - Every function returns 0 on success and a negative lrc_status on failure; the message is
+ *     available from lrc_last_error(ctx) (or lrc_last_error(NULL) for lrc_create failures).
+ *   - One lrc_ctx per (process, GPU).  A context is NOT thread-safe; callers serialise per context.
+ *   - Pointers are DEVICE pointers on ctx's GPU unless the parameter name starts with `h_`.
+ *   - All work is enqueued on the caller's `stream` (a cudaStream_t passed as void*; NULL = the
+ *     legacy default stream).  Outputs are valid once that stream has been synchronised.  The caller
+ *     owns every buffer passed in; the context owns the BVH and its scratch space.
+ *   - Ray layout: N x 6 float32 row-major [ox oy oz dx dy dz]; directions are used AS GIVEN
+ *     (not normalised) by the intersector, t is in units of |d|  (raycast_engine_cpu.py:50-51).
+ *   - Miss: t_hit = +inf, prim_id = LRC_MISS_ID.
+ *   - Closest hit: smallest t; equal t -> smallest original triangle index.  Two-sided triangles,
+ *     t >= 0.  The float32 Moller-Trumbore operation order is fixed (DESIGN.md "intersection spec").
+ *   - Triangle label: uint32 = semantic | instance << 16 (dtype contract of
+ *     containers/s3dis_sim_scene.py:581-582,630-631).
+ */
+#ifndef LRC_H
+#define LRC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LRC_MISS_ID 0xFFFFFFFFu
+#define LRC_ABI_VERSION 1
+
+typedef struct lrc_ctx lrc_ctx;
+
+typedef enum {
+    LRC_OK = 0,
+    LRC_ERR_INVALID = -1,   /* bad argument (NULL pointer, negative size, index out of range ...) */
+    LRC_ERR_CUDA = -2,      /* a CUDA runtime call failed; message holds cudaGetErrorString */
+    LRC_ERR_NO_MESH = -3,   /* a cast/scan entry point was called before lrc_set_mesh */
+    LRC_ERR_CAPACITY = -4,  /* an output buffer is too small / BVH deeper than the traversal stack */
+    LRC_ERR_NO_DEVICE = -5  /* no usable CUDA device: the engine has no CPU fallback */
+} lrc_status;
+
+/* Single-axis sensor == Indoor8LineLidarIntrinsics + IndoorLidar.get_rays
+ * (lidar/lidar_intrinsics.py:214-289, lidar/indoor_lidar.py:27-53,56-131). */
+typedef struct {
+    int32_t H;                    /* number of scan lines (len(vertical_degrees), or vertical_res) */
+    int32_t W;                    /* horizontal_res */
+    const double* h_vertical_deg; /* HOST, H entries, degrees; NULL -> uniform-fov table below   */
+    double fov_up_deg;            /* used only when h_vertical_deg == NULL (indoor_lidar.py:56-91) */
+    double fov_down_deg;
+    double max_range;             /* metres; strict '<' on the f64 distance (raycast_engine_cpu.py:95-97) */
+} lrc_single_axis;
+
+/* Dual-axis sensor == DualAxisLidarIntrinsics + DualAxisLidar.get_multi_line_rays
+ * (lidar/lidar_intrinsics.py:28-66,152-186, lidar/indoor_lidar.py:224-296). */
+typedef struct {
+    int32_t num_lines;            /* num_vertical_lines */
+    int32_t points_per_line;      /* int(point_rate*scan_duration) // num_vertical_lines */
+    double theta_min, theta_max;  /* theta_range, radians */
+    double swing_amplitude;       /* radians */
+    double swing_frequency;
+    double max_range;
+} lrc_dual_axis;
+
+/* Noise model.  The reference draws from the global numpy stream (indoor_lidar.py:270-272,292-294);
+ * the engine uses Philox4x32-10 keyed on (seed, pose index, ray index) so that results do not
+ * depend on launch geometry or on the number of GPUs.  NULL or all-zero = noise disabled. */
+typedef struct {
+    double angle_noise_std;       /* rad, added to phi and theta after the clip (dual-axis only) */
+    double dropout_probability;   /* ray kept iff u > p, BEFORE casting (dual-axis only) */
+    double range_noise_std;       /* metres, added to t before the point is reconstructed (both) */
+    uint64_t seed;
+    uint64_t pose_index_base;     /* global index of poses[0]: rank r of a sharded run passes its offset */
+} lrc_noise;
+
+/* Compacted, ray-ordered output of a scan (structure of arrays, caller-allocated, device).
+ * Frame p occupies [frame_offset[p], frame_offset[p+1]).  Any array pointer except xyz and
+ * frame_offset may be NULL (that attribute is then not produced). */
+typedef struct {
+    float* xyz;              /* capacity x 3 float32                 == points  (raycast_engine_cpu.py:111) */
+    double* incident_deg;    /* capacity      float64, degrees       == incident_angles (:100-107) */
+    uint32_t* prim_id;       /* capacity      original triangle index */
+    uint32_t* label;         /* capacity      tri_label[prim_id] (0 when the mesh has no labels) */
+    uint32_t* ray_idx;       /* capacity      index of the ray inside its frame (before dropout) */
+    int64_t* frame_offset;   /* P + 1 */
+    int64_t capacity;        /* in points; P * rays_per_pose always suffices */
+} lrc_out;
+
+typedef struct {
+    uint64_t rays;           /* rays traversed (after dropout) */
+    uint64_t nodes_visited;  /* BVH node records fetched (64 B each) */
+    uint64_t tris_tested;    /* triangle records fetched (48 B each) */
+    uint64_t hits;           /* rays with a finite t */
+} lrc_counters_t;
+
+typedef struct {
+    int64_t num_tris;
+    int64_t num_nodes;
+    int32_t max_depth;
+    int32_t reserved;
+    float scene_min[3];
+    float scene_max[3];
+    float box_pad;           /* absolute padding applied to every leaf box */
+    float sah_cost;          /* surface-area-heuristic cost of the built tree (diagnostic) */
+    int64_t bytes_nodes;
+    int64_t bytes_tris;
+} lrc_bvh_info;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+int lrc_abi_version(void);
+/* == RaycastEngineGPU.__init__ (raycast_engine/raycast_engine_gpu_simple.py:18-20). */
+int lrc_create(int device, lrc_ctx** out);
+void lrc_destroy(lrc_ctx* ctx);
+const char* lrc_last_error(const lrc_ctx* ctx);
+
+/* ---- scene ---------------------------------------------------------------------------------- */
+/* == o3d.t.geometry.RaycastingScene() + add_triangles(from_legacy(mesh))
+ *    (raycast_engine_cpu.py:46-47).  verts are float32 (the caller rounds the legacy float64
+ *    vertices exactly as from_legacy does).  Builds the LBVH (Morton codes + radix sort + Karras
+ *    hierarchy + refit) on the GPU and keeps it until the next lrc_set_mesh / lrc_destroy.
+ *    tri_label may be NULL. */
+int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const int32_t* tris, int64_t T,
+                 const uint32_t* tri_label, void* stream);
+int lrc_bvh_get_info(lrc_ctx* ctx, lrc_bvh_info* h_info);
+
+/* ---- rays_intersect_mesh -------------------------------------------------------------------- */
+/* == RaycastingScene.cast_rays -> "t_hit", "primitive_ids" (raycast_engine_cpu.py:51-53). */
+int lrc_cast_rays(lrc_ctx* ctx, const float* rays, int64_t N, float* t_hit, uint32_t* prim_id, void* stream);
+/* Exhaustive ray x triangle reference kernel on the GPU (validation of the BVH path). */
+int lrc_cast_rays_bruteforce(lrc_ctx* ctx, const float* rays, int64_t N, float* t_hit, uint32_t* prim_id, void* stream);
+/* == RaycastEngineCPU.rays_intersect_mesh (raycast_engine_cpu.py:24-73): cast, d^ = d/|d| and
+ *    p = o + d^*t in float32, ordered compaction by the hit mask.  out->frame_offset has 2 entries. */
+int lrc_rays_intersect(lrc_ctx* ctx, const float* rays, int64_t N, lrc_out* out, void* stream);
+/* == RaycastEngineCPU.lidar_intersect_mesh (raycast_engine_cpu.py:75-111) for a duck-typed lidar
+ *    whose rays were produced elsewhere: cast + range filter around h_center + incident angle. */
+int lrc_scan_rays(lrc_ctx* ctx, const float* rays, int64_t N, const double* h_center, double max_range,
+                  lrc_out* out, void* stream);
+
+/* ---- lidar_intersect_mesh, batched over a trajectory ---------------------------------------- */
+/* P poses, each a row-major 4x4 float64 matrix (Waypoint.to_pose_matrix,
+ * trajectory/trajectory_generator.py:30-44), DEVICE memory.  Rays are generated in-kernel and
+ * never written to HBM.  Per frame this is RaycastEngineCPU.lidar_intersect_mesh. */
+int lrc_scan_single_axis(lrc_ctx* ctx, const double* poses, int64_t P, const lrc_single_axis* h_sensor,
+                         const lrc_noise* h_noise, lrc_out* out, void* stream);
+int lrc_scan_dual_axis(lrc_ctx* ctx, const double* poses, int64_t P, const lrc_dual_axis* h_sensor,
+                       const lrc_noise* h_noise, lrc_out* out, void* stream);
+
+/* ---- get_rays ------------------------------------------------------------------------------- */
+/* == IndoorLidar.get_rays (indoor_lidar.py:27-53): rays H*W x 6 float32, index j*W + i. */
+int lrc_gen_rays_single_axis(lrc_ctx* ctx, const double* poses, int64_t P, const lrc_single_axis* h_sensor,
+                             float* rays, void* stream);
+/* == DualAxisLidar.get_rays (indoor_lidar.py:311-319): dense table line*ppl + k plus keep flags
+ *    (the caller drops rays whose flag is 0, as indoor_lidar.py:292-294 does). */
+int lrc_gen_rays_dual_axis(lrc_ctx* ctx, const double* poses, int64_t P, const lrc_dual_axis* h_sensor,
+                           const lrc_noise* h_noise, float* rays, uint8_t* keep, void* stream);
+
+/* ---- measurement ---------------------------------------------------------------------------- */
+/* Work counters, accumulated by cast/scan calls while counting is enabled (a separate, slower
+ * instantiation of the traversal kernel).  lrc_counters synchronises `stream` first. */
+int lrc_set_counting(lrc_ctx* ctx, int enabled);
+int lrc_counters(lrc_ctx* ctx, lrc_counters_t* h_out, int reset, void* stream);
+/* Number of kernel launches issued by this context since creation (for bench.py's gpu_launches). */
+int64_t lrc_launch_count(const lrc_ctx* ctx);
+/* Traversal kernel variant / tuning knob: 0 = default.  Unknown keys -> LRC_ERR_INVALID. */
+int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LRC_H */

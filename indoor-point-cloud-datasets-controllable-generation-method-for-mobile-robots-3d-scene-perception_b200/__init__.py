@@ -1,0 +1,32 @@
+"""
+B200-native LiDAR ray-casting engine: a drop-in for the ray-cast step of the indoor mobile-LiDAR dataset
+generator (reference ``raycast_engine/`` + ``lidar/``; called from ``s3dis_simulator.py:254-288``).
+
+The directory name contains hyphens, so import it through the alias package::
+
+    import lrc_b200 as lrc
+    engine = lrc.RaycastEngineGPU()
+    points, incident = engine.lidar_intersect_mesh(lrc.create_lidar(intrinsics, pose), mesh)
+
+Sub-packages keep the reference's module names: ``lidar`` (sensor model) and ``raycast_engine`` (engine).
+Importing the package needs neither a GPU nor the built library; creating an engine needs both.
+"""
+from . import lidar, raycast_engine, synthetic, trajectory
+from .core import (Context, NoiseConfig, ScanResult, TriangleMesh, get_context, mesh_arrays, pack_labels,
+                   rays_per_frame, unpack_labels)
+from .lidar import (DualAxisLidar, DualAxisLidarIntrinsics, Indoor8LineLidarIntrinsics, IndoorLidar, LidarIntrinsics,
+                    create_lidar, get_lidar_type)
+from .raycast_engine import RaycastEngineBase, RaycastEngineGPU
+from .trajectory import Waypoint, poses_from_waypoints, shard_range
+
+__version__ = "0.1.0"
+
+__all__ = [
+    "lidar", "raycast_engine", "synthetic", "trajectory",
+    "Context", "NoiseConfig", "ScanResult", "TriangleMesh", "get_context", "mesh_arrays", "pack_labels",
+    "unpack_labels", "rays_per_frame",
+    "LidarIntrinsics", "Indoor8LineLidarIntrinsics", "DualAxisLidarIntrinsics", "IndoorLidar", "DualAxisLidar",
+    "create_lidar", "get_lidar_type",
+    "RaycastEngineBase", "RaycastEngineGPU",
+    "Waypoint", "poses_from_waypoints", "shard_range",
+]

@@ -1,0 +1,398 @@
+"""
+Host-side plumbing between the reference-shaped Python API and the C ABI (include/lrc.h).
+
+PyTorch is used only for what the task allows it for: device memory (tensors own every buffer that
+crosses the ABI), streams and (in ``distributed.py``) ``torch.distributed``.  All geometry, ray
+generation, traversal and compaction happens inside ``csrc/liblrc.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import zlib
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+MISS_ID = nat.MISS_ID
+
+
+# --------------------------------------------------------------------------------------------------
+# mesh access
+# --------------------------------------------------------------------------------------------------
+class TriangleMesh:
+    """Minimal stand-in for ``o3d.geometry.TriangleMesh`` (Open3D is not a dependency of this engine):
+    ``vertices`` (V,3) float64, ``triangles`` (T,3) int32 and, as an extension, ``triangle_labels`` (T,)
+    uint32 = semantic | instance << 16.  Any object with ``.vertices`` / ``.triangles`` works as well."""
+
+    def __init__(self, vertices, triangles, triangle_labels=None):
+        self.vertices = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
+        self.triangles = np.ascontiguousarray(triangles, dtype=np.int32).reshape(-1, 3)
+        self.triangle_labels = None if triangle_labels is None else np.ascontiguousarray(triangle_labels, dtype=np.uint32)
+        if self.triangle_labels is not None and len(self.triangle_labels) != len(self.triangles):
+            raise ValueError("triangle_labels must have one entry per triangle")
+
+    def __repr__(self):
+        return f"TriangleMesh(V={len(self.vertices)}, T={len(self.triangles)}, labels={self.triangle_labels is not None})"
+
+
+def pack_labels(semantic, instance) -> np.ndarray:
+    """uint32 = semantic | instance << 16 (uint16/uint16 contract of reference s3dis_sim_scene.py:581-582)."""
+    return (np.asarray(semantic, dtype=np.uint32) & 0xFFFF) | ((np.asarray(instance, dtype=np.uint32) & 0xFFFF) << 16)
+
+
+def unpack_labels(label) -> Tuple[np.ndarray, np.ndarray]:
+    label = np.asarray(label, dtype=np.uint32)
+    return (label & 0xFFFF).astype(np.uint16), (label >> 16).astype(np.uint16)
+
+
+def mesh_arrays(mesh):
+    """-> (verts float32 (V,3), tris int32 (T,3), labels uint32 (T,) | None).  Vertices are rounded to
+    float32 exactly as ``o3d.t.geometry.TriangleMesh.from_legacy`` does (reference raycast_engine_cpu.py:47)."""
+    if isinstance(mesh, (tuple, list)):
+        v, f = mesh[0], mesh[1]
+        lab = mesh[2] if len(mesh) > 2 else None
+    else:
+        v, f = mesh.vertices, mesh.triangles
+        lab = getattr(mesh, "triangle_labels", None)
+    v = np.ascontiguousarray(np.asarray(v), dtype=np.float32).reshape(-1, 3)
+    f = np.ascontiguousarray(np.asarray(f), dtype=np.int32).reshape(-1, 3)
+    if lab is not None:
+        lab = np.ascontiguousarray(np.asarray(lab), dtype=np.uint32).reshape(-1)
+        if len(lab) != len(f):
+            raise ValueError("triangle_labels must have one entry per triangle")
+    return v, f, lab
+
+
+def mesh_fingerprint(mesh) -> tuple:
+    """Cheap identity of a mesh for the BVH cache: sizes plus a CRC of a strided sample of the data."""
+    if isinstance(mesh, (tuple, list)):
+        v, f = np.asarray(mesh[0]), np.asarray(mesh[1])
+    else:
+        v, f = np.asarray(mesh.vertices), np.asarray(mesh.triangles)
+    sv = max(1, v.shape[0] // 4096)
+    sf = max(1, f.shape[0] // 4096)
+    crc = zlib.crc32(np.ascontiguousarray(v[::sv]).tobytes())
+    crc = zlib.crc32(np.ascontiguousarray(f[::sf]).tobytes(), crc)
+    crc = zlib.crc32(np.ascontiguousarray(v[-1:]).tobytes(), crc)
+    return (id(mesh), v.shape[0], f.shape[0], crc)
+
+
+# --------------------------------------------------------------------------------------------------
+# sensor descriptors
+# --------------------------------------------------------------------------------------------------
+def single_axis_desc(intr) -> nat.SingleAxis:
+    """Indoor8LineLidarIntrinsics -> lrc_single_axis (duck-typed; reference indoor_lidar.py:38-51)."""
+    vd = getattr(intr, "vertical_degrees", None)
+    d = nat.SingleAxis()
+    d.W = max(1, int(intr.horizontal_res))
+    if vd is None:
+        d.H = max(1, int(intr.vertical_res))
+        d.h_vertical_deg = None
+        d._keep = None
+    else:
+        table = list(vd) if len(vd) > 0 else [0.0]          # reference indoor_lidar.py:104-106
+        arr = (C.c_double * len(table))(*[float(x) for x in table])
+        d.H = len(table)
+        d.h_vertical_deg = C.cast(arr, C.POINTER(C.c_double))
+        d._keep = arr                                         # keep the host table alive
+    d.fov_up_deg = float(intr.fov_up)
+    d.fov_down_deg = float(intr.fov_down)
+    d.max_range = float(intr.max_range)
+    return d
+
+
+def dual_axis_desc(intr) -> nat.DualAxis:
+    """DualAxisLidarIntrinsics -> lrc_dual_axis (reference indoor_lidar.py:241-252)."""
+    n_pts = int(intr.point_rate * intr.scan_duration)
+    lines = int(intr.num_vertical_lines)
+    return nat.DualAxis(num_lines=lines, points_per_line=n_pts // lines,
+                        theta_min=float(intr.theta_range[0]), theta_max=float(intr.theta_range[1]),
+                        swing_amplitude=float(intr.swing_amplitude), swing_frequency=float(intr.swing_frequency),
+                        max_range=float(intr.max_range))
+
+
+def is_dual_axis(intr) -> bool:
+    return hasattr(intr, "num_vertical_lines") and hasattr(intr, "swing_amplitude")
+
+
+def rays_per_frame(intr) -> int:
+    if is_dual_axis(intr):
+        d = dual_axis_desc(intr)
+        return d.num_lines * d.points_per_line
+    d = single_axis_desc(intr)
+    return d.H * d.W
+
+
+@dataclass
+class NoiseConfig:
+    """Counter-based (Philox) noise; all zero = disabled = the bit-exact parity configuration."""
+    angle_noise_std: float = 0.0
+    dropout_probability: float = 0.0
+    range_noise_std: float = 0.0
+    seed: int = 0
+    pose_index_base: int = 0
+
+    def struct(self) -> nat.Noise:
+        return nat.Noise(float(self.angle_noise_std), float(self.dropout_probability), float(self.range_noise_std),
+                         int(self.seed) & 0xFFFFFFFFFFFFFFFF, int(self.pose_index_base))
+
+    @classmethod
+    def from_intrinsics(cls, intr, seed: int = 0, pose_index_base: int = 0) -> "NoiseConfig":
+        """The noise the reference applies on the simulation path: angle noise + dropout for the dual-axis
+        sensor (indoor_lidar.py:270-272,292-294); nothing for the single-axis sensor (add_noise is dead code)."""
+        if is_dual_axis(intr):
+            return cls(float(intr.angle_noise_std), float(intr.dropout_probability), 0.0, seed, pose_index_base)
+        return cls(0.0, 0.0, 0.0, seed, pose_index_base)
+
+
+# --------------------------------------------------------------------------------------------------
+# results
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class ScanResult:
+    """Compacted, ray-ordered hits of P frames (device tensors).  Frame p is [frame_offset[p], frame_offset[p+1])."""
+    points: torch.Tensor          # (M,3) float32
+    incident: torch.Tensor        # (M,)  float64 degrees
+    prim_id: torch.Tensor         # (M,)  int32 holding uint32 bits
+    label: torch.Tensor           # (M,)  int32 holding uint32 bits (sem | ins << 16)
+    ray_idx: torch.Tensor         # (M,)  int32
+    frame_offset: torch.Tensor    # (P+1,) int64, host copy in frame_offset_host
+    frame_offset_host: np.ndarray
+
+    @property
+    def num_points(self) -> int:
+        return int(self.frame_offset_host[-1])
+
+    @property
+    def num_frames(self) -> int:
+        return len(self.frame_offset_host) - 1
+
+    def frame(self, p: int):
+        """(points (m,3) f32, incident (m,) f64) of frame p as numpy -- the reference's return value."""
+        a, b = int(self.frame_offset_host[p]), int(self.frame_offset_host[p + 1])
+        return self.points[a:b].cpu().numpy(), self.incident[a:b].cpu().numpy()
+
+    def numpy(self) -> dict:
+        return {
+            "points": self.points.cpu().numpy(),
+            "incident": self.incident.cpu().numpy(),
+            "prim_id": self.prim_id.cpu().numpy().view(np.uint32),
+            "label": self.label.cpu().numpy().view(np.uint32),
+            "ray_idx": self.ray_idx.cpu().numpy().view(np.uint32),
+            "frame_offset": self.frame_offset_host.copy(),
+        }
+
+
+# --------------------------------------------------------------------------------------------------
+# context
+# --------------------------------------------------------------------------------------------------
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Context:
+    """One ``lrc_ctx`` (one GPU).  Not thread-safe; all work goes to torch's current stream."""
+
+    def __init__(self, device: Optional[int] = None):
+        self._lib = nat.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device visible: the LiDAR ray-casting engine has no CPU fallback")
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        h = C.c_void_p()
+        nat.check(None, self._lib.lrc_create(self.device_index, C.byref(h)))
+        self._h = h
+        self._mesh_key = None
+        self._mesh_refs = None
+        self.num_tris = 0
+        self.has_labels = False
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.lrc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- helpers ----
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self, arr, dtype) -> torch.Tensor:
+        if isinstance(arr, torch.Tensor):
+            return arr.to(device=self.device, dtype=dtype).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(arr)).to(device=self.device, dtype=dtype, non_blocking=False).contiguous()
+
+    def launch_count(self) -> int:
+        return int(self._lib.lrc_launch_count(self._h))
+
+    def set_option(self, key: str, value: int) -> None:
+        nat.check(self._h, self._lib.lrc_set_option(self._h, key.encode(), int(value)))
+
+    # ---- scene ----
+    def set_mesh_arrays(self, verts, tris, labels=None) -> None:
+        """Upload float32 vertices / int32 indices / uint32 labels and build the LBVH on the GPU."""
+        with torch.cuda.device(self.device):
+            v = self._dev(verts, torch.float32).reshape(-1, 3)
+            f = self._dev(tris, torch.int32).reshape(-1, 3)
+            lab = None
+            if labels is not None:
+                lab_np = labels if isinstance(labels, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(labels, dtype=np.uint32).view(np.int32))
+                lab = lab_np.to(device=self.device).contiguous()
+                if lab.numel() != f.shape[0]:
+                    raise ValueError("labels must have one entry per triangle")
+            nat.check(self._h, self._lib.lrc_set_mesh(self._h, _ptr(v), v.shape[0], _ptr(f), f.shape[0], _ptr(lab), self._stream()))
+            self.num_tris = int(f.shape[0])
+            self.has_labels = lab is not None
+            self._mesh_key = None
+
+    def set_mesh(self, mesh, cache: bool = True) -> bool:
+        """Build (or reuse) the BVH of ``mesh``.  Returns True when a build happened."""
+        key = mesh_fingerprint(mesh) if cache else None
+        if cache and key == self._mesh_key and self._mesh_key is not None:
+            return False
+        v, f, lab = mesh_arrays(mesh)
+        self.set_mesh_arrays(v, f, lab)
+        self._mesh_key = key
+        return True
+
+    def bvh_info(self) -> dict:
+        info = nat.BvhInfo()
+        nat.check(self._h, self._lib.lrc_bvh_get_info(self._h, C.byref(info)))
+        return {
+            "num_tris": info.num_tris, "num_nodes": info.num_nodes, "max_depth": info.max_depth,
+            "scene_min": list(info.scene_min), "scene_max": list(info.scene_max), "box_pad": info.box_pad,
+            "sah_cost": info.sah_cost, "bytes_nodes": info.bytes_nodes, "bytes_tris": info.bytes_tris,
+        }
+
+    # ---- counters ----
+    def set_counting(self, enabled: bool) -> None:
+        nat.check(self._h, self._lib.lrc_set_counting(self._h, 1 if enabled else 0))
+
+    def counters(self, reset: bool = True) -> dict:
+        c = nat.Counters()
+        nat.check(self._h, self._lib.lrc_counters(self._h, C.byref(c), 1 if reset else 0, self._stream()))
+        return {"rays": c.rays, "nodes_visited": c.nodes_visited, "tris_tested": c.tris_tested, "hits": c.hits}
+
+    # ---- rays_intersect_mesh family ----
+    def cast_rays(self, rays, bruteforce: bool = False):
+        """rays (N,6) float32 (tensor or ndarray) -> (t_hit float32 [N], prim_id int32 [N] holding uint32 bits)."""
+        with torch.cuda.device(self.device):
+            r = self._dev(rays, torch.float32).reshape(-1, 6)
+            n = r.shape[0]
+            t = torch.empty(n, dtype=torch.float32, device=self.device)
+            pid = torch.empty(n, dtype=torch.int32, device=self.device)
+            fn = self._lib.lrc_cast_rays_bruteforce if bruteforce else self._lib.lrc_cast_rays
+            nat.check(self._h, fn(self._h, _ptr(r), n, _ptr(t), _ptr(pid), self._stream()))
+            return t, pid
+
+    def _alloc_out(self, capacity: int, frames: int, full: bool = True):
+        dev = self.device
+        cap = max(1, capacity)
+        bufs = {
+            "xyz": torch.empty((cap, 3), dtype=torch.float32, device=dev),
+            "incident": torch.empty(cap, dtype=torch.float64, device=dev) if full else None,
+            "prim": torch.empty(cap, dtype=torch.int32, device=dev) if full else None,
+            "label": torch.empty(cap, dtype=torch.int32, device=dev) if full else None,
+            "ray": torch.empty(cap, dtype=torch.int32, device=dev) if full else None,
+            "off": torch.zeros(frames + 1, dtype=torch.int64, device=dev),
+        }
+        out = nat.Out(_ptr(bufs["xyz"]), _ptr(bufs["incident"]), _ptr(bufs["prim"]), _ptr(bufs["label"]),
+                      _ptr(bufs["ray"]), _ptr(bufs["off"]), cap)
+        return bufs, out
+
+    def _finish(self, bufs) -> ScanResult:
+        off_host = bufs["off"].cpu().numpy()          # synchronises the stream
+        m = int(off_host[-1])
+        e32 = torch.empty(0, dtype=torch.int32, device=self.device)
+        return ScanResult(
+            points=bufs["xyz"][:m],
+            incident=bufs["incident"][:m] if bufs["incident"] is not None else torch.empty(0, dtype=torch.float64, device=self.device),
+            prim_id=bufs["prim"][:m] if bufs["prim"] is not None else e32,
+            label=bufs["label"][:m] if bufs["label"] is not None else e32,
+            ray_idx=bufs["ray"][:m] if bufs["ray"] is not None else e32,
+            frame_offset=bufs["off"], frame_offset_host=off_host)
+
+    def rays_intersect(self, rays) -> ScanResult:
+        """== RaycastEngineCPU.rays_intersect_mesh core: hit points in ray order (no range filter)."""
+        with torch.cuda.device(self.device):
+            r = self._dev(rays, torch.float32).reshape(-1, 6)
+            bufs, out = self._alloc_out(r.shape[0], 1)
+            nat.check(self._h, self._lib.lrc_rays_intersect(self._h, _ptr(r), r.shape[0], C.byref(out), self._stream()))
+            return self._finish(bufs)
+
+    def scan_rays(self, rays, center, max_range: float) -> ScanResult:
+        """== RaycastEngineCPU.lidar_intersect_mesh for explicit rays of one frame."""
+        with torch.cuda.device(self.device):
+            r = self._dev(rays, torch.float32).reshape(-1, 6)
+            c = (C.c_double * 3)(*[float(x) for x in center])
+            bufs, out = self._alloc_out(r.shape[0], 1)
+            nat.check(self._h, self._lib.lrc_scan_rays(self._h, _ptr(r), r.shape[0], c, float(max_range), C.byref(out), self._stream()))
+            return self._finish(bufs)
+
+    # ---- batched trajectory scan ----
+    def scan_enqueue(self, poses_dev: torch.Tensor, intr, noise: Optional[NoiseConfig], bufs=None):
+        """Enqueue a P-pose scan on the current stream; returns (bufs, out struct) without synchronising."""
+        P = int(poses_dev.shape[0])
+        n_frame = rays_per_frame(intr)
+        if bufs is None:
+            bufs, out = self._alloc_out(P * n_frame, P)
+        else:
+            out = nat.Out(_ptr(bufs["xyz"]), _ptr(bufs["incident"]), _ptr(bufs["prim"]), _ptr(bufs["label"]),
+                          _ptr(bufs["ray"]), _ptr(bufs["off"]), bufs["xyz"].shape[0])
+        nz = noise.struct() if noise is not None else None
+        nzp = C.byref(nz) if nz is not None else None
+        if is_dual_axis(intr):
+            d = dual_axis_desc(intr)
+            nat.check(self._h, self._lib.lrc_scan_dual_axis(self._h, _ptr(poses_dev), P, C.byref(d), nzp, C.byref(out), self._stream()))
+        else:
+            d = single_axis_desc(intr)
+            nat.check(self._h, self._lib.lrc_scan_single_axis(self._h, _ptr(poses_dev), P, C.byref(d), nzp, C.byref(out), self._stream()))
+        return bufs, out
+
+    def scan(self, poses, intr, noise: Optional[NoiseConfig] = None) -> ScanResult:
+        """poses: (P,4,4) float64 (ndarray or tensor).  One fused launch sequence for the whole trajectory."""
+        with torch.cuda.device(self.device):
+            p = self._dev(poses, torch.float64).reshape(-1, 16)
+            bufs, _ = self.scan_enqueue(p, intr, noise)
+            return self._finish(bufs)
+
+    # ---- get_rays ----
+    def gen_rays(self, poses, intr, noise: Optional[NoiseConfig] = None):
+        """-> (rays (P*N,6) float32 tensor, keep (P*N,) uint8 tensor | None)."""
+        with torch.cuda.device(self.device):
+            p = self._dev(poses, torch.float64).reshape(-1, 16)
+            P = p.shape[0]
+            n = P * rays_per_frame(intr)
+            rays = torch.empty((max(n, 1), 6), dtype=torch.float32, device=self.device)[:n]
+            if is_dual_axis(intr):
+                d = dual_axis_desc(intr)
+                keep = torch.empty(max(n, 1), dtype=torch.uint8, device=self.device)[:n]
+                nz = noise.struct() if noise is not None else None
+                nat.check(self._h, self._lib.lrc_gen_rays_dual_axis(self._h, _ptr(p), P, C.byref(d), C.byref(nz) if nz is not None else None,
+                                                                     _ptr(rays), _ptr(keep), self._stream()))
+                return rays, keep
+            d = single_axis_desc(intr)
+            nat.check(self._h, self._lib.lrc_gen_rays_single_axis(self._h, _ptr(p), P, C.byref(d), _ptr(rays), self._stream()))
+            return rays, None
+
+
+_contexts = {}
+
+
+def get_context(device: Optional[int] = None) -> Context:
+    """Process-wide context per GPU (created on first use)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device visible: the LiDAR ray-casting engine has no CPU fallback")
+    idx = torch.cuda.current_device() if device is None else int(device)
+    if idx not in _contexts:
+        _contexts[idx] = Context(idx)
+    return _contexts[idx]

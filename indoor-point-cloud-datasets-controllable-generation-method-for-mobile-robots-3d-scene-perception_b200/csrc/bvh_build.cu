@@ -1,0 +1,497 @@
+// bvh_build.cu -- GPU construction of the linear BVH that replaces
+//     o3d.t.geometry.RaycastingScene() + add_triangles(...)   (reference raycast_engine_cpu.py:46-47)
+//
+// Pipeline (all on the caller's stream, one synchronisation at the end to read back tree depth):
+//   k_scene_bounds   vertex-index validation + scene AABB (warp shuffles + ordered-int atomics)
+//   k_morton         63-bit Morton code of each triangle's box centre (cubic cells, 21 bits/axis)
+//   radix sort       hand-written LSD sort of (u64 key, u32 triangle id), 8 bits x 8 passes:
+//                    k_rs_hist -> k_rs_scan -> k_rs_scatter (stable multi-split by warp match)
+//   k_leaf_init      48 B triangle records (v0|id, e1, e2) in Morton order + padded leaf boxes
+//   k_hierarchy      Karras 2012 binary radix tree over the sorted keys (ties broken by position)
+//   k_refit          bottom-up AABB union with atomic arrival flags; the second arriver writes the
+//                    64 B node record (both child boxes + child links), tree height and SAH sum
+//
+// HBM layout produced:
+//   nodes: (T-1) x 4 float4   n0=(c0.lo.xyz, c0.hi.x) n1=(c0.hi.yz, c1.lo.xy) n2=(c1.lo.z, c1.hi.xyz)
+//                             n3=(link0, link1, 0, 0) as int bits; link >= 0 internal, < 0 leaf ~slot
+//   tris : T x 3 float4       (v0.xyz, orig id) (e1.xyz, 0) (e2.xyz, 0), slot = Morton rank
+#include "common.cuh"
+
+namespace {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_CHUNKS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_CHUNKS;
+
+struct BuildMeta {            // lives in device memory during a build
+    unsigned lo[3], hi[3];    // ordered-uint encoded scene bounds
+    int bad_index;            // set when a triangle references a vertex outside [0, V)
+    int height;               // tree height (edges on the longest root->leaf path)
+    double area_sum;          // sum of internal-node surface areas (for the SAH diagnostic)
+    float root_lo[3], root_hi[3];
+};
+
+__global__ void k_meta_init(BuildMeta* m)
+{
+    for (int k = 0; k < 3; ++k) { m->lo[k] = 0xffffffffu; m->hi[k] = 0u; }
+    m->bad_index = 0;
+    m->height = 0;
+    m->area_sum = 0.0;
+}
+
+__global__ void k_scene_bounds(const float* __restrict__ verts, int64_t V, const int32_t* __restrict__ tris, int64_t T,
+                               BuildMeta* meta)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {LRC_INF, LRC_INF, LRC_INF}, hi[3] = {-LRC_INF, -LRC_INF, -LRC_INF};
+    bool bad = false;
+    if (i < T) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            int64_t v = tris[3 * i + c];
+            if (v < 0 || v >= V) { bad = true; continue; }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                float x = verts[3 * v + k];
+                lo[k] = fminf(lo[k], x);
+                hi[k] = fmaxf(hi[k], x);
+            }
+        }
+    }
+    if (__any_sync(0xffffffffu, bad) && bad) atomicExch(&meta->bad_index, 1);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float l = lo[k], h = hi[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o));
+            h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, o));
+        }
+        if (lane_id() == 0 && l <= h) {
+            atomicMin(&meta->lo[k], f2ord(l));
+            atomicMax(&meta->hi[k], f2ord(h));
+        }
+    }
+}
+
+__device__ __forceinline__ uint64_t expand21(uint32_t v)
+{
+    uint64_t x = v & 0x1fffffu;
+    x = (x | x << 32) & 0x001f00000000ffffull;
+    x = (x | x << 16) & 0x001f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+__global__ void k_morton(const float* __restrict__ verts, const int32_t* __restrict__ tris, int64_t T,
+                         const BuildMeta* __restrict__ meta, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T) return;
+    float slo[3], ext = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        slo[k] = ord2f(meta->lo[k]);
+        ext = fmaxf(ext, ord2f(meta->hi[k]) - slo[k]);
+    }
+    float scale = ext > 0.f ? 2097152.0f / ext : 0.f;   // 2^21 cubic cells along the longest axis
+    uint32_t q[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float a = verts[3 * (int64_t)tris[3 * i + 0] + k];
+        float b = verts[3 * (int64_t)tris[3 * i + 1] + k];
+        float c = verts[3 * (int64_t)tris[3 * i + 2] + k];
+        float cen = 0.5f * (fminf(a, fminf(b, c)) + fmaxf(a, fmaxf(b, c)));
+        float f = (cen - slo[k]) * scale;
+        f = fminf(fmaxf(f, 0.f), 2097151.0f);
+        q[k] = (uint32_t)f;
+    }
+    keys[i] = (expand21(q[0]) << 2) | (expand21(q[1]) << 1) | expand21(q[2]);
+    vals[i] = (uint32_t)i;
+}
+
+// ---- LSD radix sort -----------------------------------------------------------------------------
+// Tile = 4096 keys per block; warp w owns 512 consecutive keys and walks them 32 at a time, so the
+// (warp, chunk, lane) order IS the input order and ranks computed from it are stable.
+__device__ __forceinline__ void rs_count_tile(const uint64_t* __restrict__ keys, int64_t n, int shift,
+                                              int64_t tile_start, unsigned (*hist)[256])
+{
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&hist[0][0])[i] = 0u;
+    __syncthreads();
+    const int64_t base = tile_start + (int64_t)w * (32 * RS_CHUNKS);
+    for (int c = 0; c < RS_CHUNKS; ++c) {
+        int64_t idx = base + c * 32 + lane;
+        bool valid = idx < n;
+        unsigned digit = valid ? (unsigned)((keys[idx] >> shift) & 255ull) : 256u;
+        unsigned m = __match_any_sync(0xffffffffu, digit);
+        if (valid && lane == (unsigned)(__ffs(m) - 1)) hist[w][digit] += __popc(m);
+        __syncwarp();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t* __restrict__ keys, int64_t n, int shift,
+                                                        unsigned* __restrict__ block_hist, int nb)
+{
+    __shared__ unsigned hist[RS_WARPS][256];
+    rs_count_tile(keys, n, shift, (int64_t)blockIdx.x * RS_TILE, hist);
+    unsigned s = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) s += hist[w][threadIdx.x];
+    block_hist[(size_t)threadIdx.x * nb + blockIdx.x] = s;   // digit-major
+}
+
+__global__ void __launch_bounds__(1024) k_rs_scan(unsigned* __restrict__ a, int64_t M)
+{
+    __shared__ unsigned warp_sums[32];
+    __shared__ unsigned carry;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0u;
+    __syncthreads();
+    for (int64_t base = 0; base < M; base += 1024) {
+        int64_t idx = base + threadIdx.x;
+        unsigned v = idx < M ? a[idx] : 0u;
+        unsigned incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            unsigned s = warp_sums[lane], si = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned t = __shfl_up_sync(0xffffffffu, si, o);
+                if (lane >= o) si += t;
+            }
+            warp_sums[lane] = si - s;
+        }
+        __syncthreads();
+        unsigned excl = incl - v + warp_sums[w] + carry;
+        if (idx < M) a[idx] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+k_rs_scatter(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out,
+             uint32_t* __restrict__ vals_out, int64_t n, int shift, const unsigned* __restrict__ scanned, int nb)
+{
+    __shared__ unsigned hist[RS_WARPS][256];
+    const int64_t tile_start = (int64_t)blockIdx.x * RS_TILE;
+    rs_count_tile(keys_in, n, shift, tile_start, hist);
+    {   // per-digit: turn warp counts into global base offsets
+        unsigned run = scanned[(size_t)threadIdx.x * nb + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            unsigned c = hist[w][threadIdx.x];
+            hist[w][threadIdx.x] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t base = tile_start + (int64_t)w * (32 * RS_CHUNKS);
+    for (int c = 0; c < RS_CHUNKS; ++c) {
+        int64_t idx = base + c * 32 + lane;
+        bool valid = idx < n;
+        uint64_t key = valid ? keys_in[idx] : 0ull;
+        unsigned digit = valid ? (unsigned)((key >> shift) & 255ull) : 256u;
+        unsigned m = __match_any_sync(0xffffffffu, digit);
+        unsigned rank = __popc(m & ((1u << lane) - 1u));
+        unsigned dst = 0;
+        if (valid) dst = hist[w][digit] + rank;
+        __syncwarp();
+        if (valid && lane == (unsigned)(__ffs(m) - 1)) hist[w][digit] += __popc(m);
+        __syncwarp();
+        if (valid) {
+            keys_out[dst] = key;
+            vals_out[dst] = vals_in[idx];
+        }
+    }
+}
+
+// ---- leaves -------------------------------------------------------------------------------------
+__global__ void k_leaf_init(const float* __restrict__ verts, const int32_t* __restrict__ tris, int64_t T,
+                            const uint32_t* __restrict__ sorted_ids, float pad, float4* __restrict__ tri_rec,
+                            float4* __restrict__ leaf_lo, float4* __restrict__ leaf_hi)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T) return;
+    uint32_t id = sorted_ids[i];
+    float a[3], b[3], c[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        a[k] = verts[3 * (int64_t)tris[3 * (int64_t)id + 0] + k];
+        b[k] = verts[3 * (int64_t)tris[3 * (int64_t)id + 1] + k];
+        c[k] = verts[3 * (int64_t)tris[3 * (int64_t)id + 2] + k];
+    }
+    // e1 = v1 - v0, e2 = v2 - v0: one IEEE subtraction each -- part of the intersection spec
+    tri_rec[3 * i + 0] = make_float4(a[0], a[1], a[2], __uint_as_float(id));
+    tri_rec[3 * i + 1] = make_float4(__fsub_rn(b[0], a[0]), __fsub_rn(b[1], a[1]), __fsub_rn(b[2], a[2]), 0.f);
+    tri_rec[3 * i + 2] = make_float4(__fsub_rn(c[0], a[0]), __fsub_rn(c[1], a[1]), __fsub_rn(c[2], a[2]), 0.f);
+    leaf_lo[i] = make_float4(fminf(a[0], fminf(b[0], c[0])) - pad, fminf(a[1], fminf(b[1], c[1])) - pad,
+                             fminf(a[2], fminf(b[2], c[2])) - pad, 0.f);
+    leaf_hi[i] = make_float4(fmaxf(a[0], fmaxf(b[0], c[0])) + pad, fmaxf(a[1], fmaxf(b[1], c[1])) + pad,
+                             fmaxf(a[2], fmaxf(b[2], c[2])) + pad, 0.f);
+}
+
+// ---- Karras 2012 --------------------------------------------------------------------------------
+__device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, int i, int j)
+{
+    if (j < 0 || j >= n) return -1;
+    uint64_t a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz(i ^ j);
+    return __clzll((long long)(a ^ b));
+}
+
+__global__ void k_hierarchy(const uint64_t* __restrict__ keys, int n, int2* __restrict__ children,
+                            int* __restrict__ parent_node, int* __restrict__ parent_leaf)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta(keys, n, i, j);
+    int s = 0;
+    for (int t = (l + 1) >> 1;; t = (t + 1) >> 1) {
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+        if (t == 1) break;
+    }
+    int gamma = i + s * d + min(d, 0);
+    int lo = min(i, j), hi = max(i, j);
+    int left = (lo == gamma) ? ~gamma : gamma;
+    int right = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+    children[i] = make_int2(left, right);
+    if (left < 0) parent_leaf[~left] = i; else parent_node[left] = i;
+    if (right < 0) parent_leaf[~right] = i; else parent_node[right] = i;
+    if (i == 0) parent_node[0] = -1;
+}
+
+__device__ __forceinline__ void load_box(int link, const float4* leaf_lo, const float4* leaf_hi, const float4* node_lo,
+                                         const float4* node_hi, float4& lo, float4& hi)
+{
+    // __ldcg: these boxes may have been written by another SM moments ago -- bypass L1
+    if (link < 0) { lo = __ldcg(&leaf_lo[~link]); hi = __ldcg(&leaf_hi[~link]); }
+    else { lo = __ldcg(&node_lo[link]); hi = __ldcg(&node_hi[link]); }
+}
+
+__global__ void k_refit(int n, const int* __restrict__ parent_leaf, const int* __restrict__ parent_node,
+                        const int2* __restrict__ children, const float4* leaf_lo, const float4* leaf_hi, float4* node_lo,
+                        float4* node_hi, int* flags, float4* __restrict__ nodes_out, BuildMeta* meta)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int cur = parent_leaf[i];
+    while (cur >= 0) {
+        if (atomicAdd(&flags[cur], 1) == 0) return;   // first arrival: the sibling subtree is not finished yet
+        int2 ch = children[cur];
+        float4 l0, h0, l1, h1;
+        load_box(ch.x, leaf_lo, leaf_hi, node_lo, node_hi, l0, h0);
+        load_box(ch.y, leaf_lo, leaf_hi, node_lo, node_hi, l1, h1);
+        float height = 1.f + fmaxf(l0.w, l1.w);        // .w of a box's lo carries the subtree height
+        float4 lo = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), height);
+        float4 hi = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.f);
+        node_lo[cur] = lo;
+        node_hi[cur] = hi;
+        nodes_out[4 * (int64_t)cur + 0] = make_float4(l0.x, l0.y, l0.z, h0.x);
+        nodes_out[4 * (int64_t)cur + 1] = make_float4(h0.y, h0.z, l1.x, l1.y);
+        nodes_out[4 * (int64_t)cur + 2] = make_float4(l1.z, h1.x, h1.y, h1.z);
+        nodes_out[4 * (int64_t)cur + 3] = make_float4(__int_as_float(ch.x), __int_as_float(ch.y), 0.f, 0.f);
+        float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z;
+        atomicAdd(&meta->area_sum, (double)(2.f * (ex * ey + ey * ez + ez * ex)));
+        int up = parent_node[cur];
+        if (up < 0) {
+            meta->height = (int)height;
+            meta->root_lo[0] = lo.x; meta->root_lo[1] = lo.y; meta->root_lo[2] = lo.z;
+            meta->root_hi[0] = hi.x; meta->root_hi[1] = hi.y; meta->root_hi[2] = hi.z;
+        }
+        __threadfence();
+        cur = up;
+    }
+}
+
+// T == 1: a root record whose two links both point at the only leaf (testing it twice is harmless)
+__global__ void k_single_leaf_root(const float4* leaf_lo, const float4* leaf_hi, float4* nodes_out, BuildMeta* meta)
+{
+    float4 l = leaf_lo[0], h = leaf_hi[0];
+    nodes_out[0] = make_float4(l.x, l.y, l.z, h.x);
+    nodes_out[1] = make_float4(h.y, h.z, l.x, l.y);
+    nodes_out[2] = make_float4(l.z, h.x, h.y, h.z);
+    nodes_out[3] = make_float4(__int_as_float(~0), __int_as_float(~0), 0.f, 0.f);
+    meta->height = 1;
+    float ex = h.x - l.x, ey = h.y - l.y, ez = h.z - l.z;
+    meta->area_sum = 2.0 * (ex * ey + ey * ez + ez * ex);
+    meta->root_lo[0] = l.x; meta->root_lo[1] = l.y; meta->root_lo[2] = l.z;
+    meta->root_hi[0] = h.x; meta->root_hi[1] = h.y; meta->root_hi[2] = h.z;
+}
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------------------
+extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const int32_t* tris, int64_t T,
+                            const uint32_t* tri_label, void* stream_)
+{
+    if (!ctx) return lrc_fail(nullptr, LRC_ERR_INVALID, "lrc_set_mesh: ctx is NULL");
+    if (V < 0 || T < 0 || T >= (int64_t)1 << 30) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_mesh: bad V/T (T must be < 2^30)");
+    if ((T > 0) && (!verts || !tris)) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_mesh: verts/tris is NULL");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LRC_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->has_mesh = false;
+    ctx->T = T;
+    ctx->V = V;
+    ctx->has_labels = tri_label != nullptr;
+    memset(&ctx->info, 0, sizeof ctx->info);
+    if (T == 0) {   // an empty scene is legal: every ray misses
+        ctx->has_mesh = true;
+        return LRC_OK;
+    }
+    const int64_t n_nodes = T > 1 ? T - 1 : 1;
+    if ((size_t)(n_nodes * 4) > ctx->nodes_cap) {
+        if (ctx->nodes) LRC_CUDA(ctx, cudaFree(ctx->nodes));
+        ctx->nodes = nullptr; ctx->nodes_cap = 0;
+        LRC_CUDA(ctx, cudaMalloc((void**)&ctx->nodes, sizeof(float4) * 4 * n_nodes));
+        ctx->nodes_cap = (size_t)(n_nodes * 4);
+    }
+    if ((size_t)(T * 3) > ctx->tris_cap) {
+        if (ctx->tris) LRC_CUDA(ctx, cudaFree(ctx->tris));
+        ctx->tris = nullptr; ctx->tris_cap = 0;
+        LRC_CUDA(ctx, cudaMalloc((void**)&ctx->tris, sizeof(float4) * 3 * T));
+        ctx->tris_cap = (size_t)(T * 3);
+    }
+    if ((size_t)T > ctx->labels_cap) {
+        if (ctx->labels) LRC_CUDA(ctx, cudaFree(ctx->labels));
+        ctx->labels = nullptr; ctx->labels_cap = 0;
+        LRC_CUDA(ctx, cudaMalloc((void**)&ctx->labels, sizeof(uint32_t) * T));
+        ctx->labels_cap = (size_t)T;
+    }
+    if (tri_label) LRC_CUDA(ctx, cudaMemcpyAsync(ctx->labels, tri_label, sizeof(uint32_t) * T, cudaMemcpyDeviceToDevice, stream));
+    else LRC_CUDA(ctx, cudaMemsetAsync(ctx->labels, 0, sizeof(uint32_t) * T, stream));
+
+    // ---- carve the build scratch ----
+    const int nb = (int)((T + RS_TILE - 1) / RS_TILE);
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    size_t o_meta = carve(sizeof(BuildMeta));
+    size_t o_k0 = carve(sizeof(uint64_t) * T), o_k1 = carve(sizeof(uint64_t) * T);
+    size_t o_v0 = carve(sizeof(uint32_t) * T), o_v1 = carve(sizeof(uint32_t) * T);
+    size_t o_hist = carve(sizeof(unsigned) * 256 * (size_t)nb);
+    size_t o_llo = carve(sizeof(float4) * T), o_lhi = carve(sizeof(float4) * T);
+    size_t o_nlo = carve(sizeof(float4) * n_nodes), o_nhi = carve(sizeof(float4) * n_nodes);
+    size_t o_pl = carve(sizeof(int) * T), o_pn = carve(sizeof(int) * n_nodes);
+    size_t o_ch = carve(sizeof(int2) * n_nodes), o_fl = carve(sizeof(int) * n_nodes);
+    int rc = lrc_grow(ctx, &ctx->scratch, &ctx->scratch_bytes, off);
+    if (rc) return rc;
+    char* base = (char*)ctx->scratch;
+    BuildMeta* meta = (BuildMeta*)(base + o_meta);
+    uint64_t* k0 = (uint64_t*)(base + o_k0); uint64_t* k1 = (uint64_t*)(base + o_k1);
+    uint32_t* v0 = (uint32_t*)(base + o_v0); uint32_t* v1 = (uint32_t*)(base + o_v1);
+    unsigned* hist = (unsigned*)(base + o_hist);
+    float4* leaf_lo = (float4*)(base + o_llo); float4* leaf_hi = (float4*)(base + o_lhi);
+    float4* node_lo = (float4*)(base + o_nlo); float4* node_hi = (float4*)(base + o_nhi);
+    int* parent_leaf = (int*)(base + o_pl); int* parent_node = (int*)(base + o_pn);
+    int2* children = (int2*)(base + o_ch); int* flags = (int*)(base + o_fl);
+
+    const int TB = 256;
+    const unsigned gT = (unsigned)((T + TB - 1) / TB);
+    k_meta_init<<<1, 1, 0, stream>>>(meta);
+    LRC_CHECK_LAUNCH(ctx, "k_meta_init");
+    k_scene_bounds<<<gT, TB, 0, stream>>>(verts, V, tris, T, meta);
+    LRC_CHECK_LAUNCH(ctx, "k_scene_bounds");
+
+    BuildMeta hm;
+    LRC_CUDA(ctx, cudaMemcpyAsync(&hm, meta, sizeof hm, cudaMemcpyDeviceToHost, stream));
+    LRC_CUDA(ctx, cudaStreamSynchronize(stream));
+    if (hm.bad_index) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_mesh: a triangle references a vertex outside [0, V)");
+    float slo[3], shi[3], ext = 0.f, amax = 0.f;
+    for (int k = 0; k < 3; ++k) {
+        unsigned ul = hm.lo[k], uh = hm.hi[k];
+        uint32_t bl = (ul & 0x80000000u) ? (ul & 0x7fffffffu) : ~ul;
+        uint32_t bh = (uh & 0x80000000u) ? (uh & 0x7fffffffu) : ~uh;
+        memcpy(&slo[k], &bl, 4);
+        memcpy(&shi[k], &bh, 4);
+        if (!(slo[k] == slo[k]) || !(shi[k] == shi[k]) || slo[k] - slo[k] != 0.f || shi[k] - shi[k] != 0.f)
+            return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_mesh: non-finite vertex coordinate");
+        ext = fmaxf(ext, shi[k] - slo[k]);
+        amax = fmaxf(amax, fmaxf(fabsf(slo[k]), fabsf(shi[k])));
+    }
+    // Leaf boxes are padded by 2^-17 of the scene scale (0.19 mm for a 25 m room): float32 rounding of
+    // the slab test (~1e-6 m) and of the Moller-Trumbore acceptance can then never cull a valid hit.
+    const float pad = ldexpf(fmaxf(ext, amax), -17);
+
+    k_morton<<<gT, TB, 0, stream>>>(verts, tris, T, meta, k0, v0);
+    LRC_CHECK_LAUNCH(ctx, "k_morton");
+    uint64_t *kin = k0, *kout = k1;
+    uint32_t *vin = v0, *vout = v1;
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = 8 * pass;
+        k_rs_hist<<<nb, RS_THREADS, 0, stream>>>(kin, T, shift, hist, nb);
+        LRC_CHECK_LAUNCH(ctx, "k_rs_hist");
+        k_rs_scan<<<1, 1024, 0, stream>>>(hist, (int64_t)256 * nb);
+        LRC_CHECK_LAUNCH(ctx, "k_rs_scan");
+        k_rs_scatter<<<nb, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, T, shift, hist, nb);
+        LRC_CHECK_LAUNCH(ctx, "k_rs_scatter");
+        uint64_t* tk = kin; kin = kout; kout = tk;
+        uint32_t* tv = vin; vin = vout; vout = tv;
+    }
+    // after an even number of passes the sorted data is back in (k0, v0) == (kin, vin)
+    k_leaf_init<<<gT, TB, 0, stream>>>(verts, tris, T, vin, pad, ctx->tris, leaf_lo, leaf_hi);
+    LRC_CHECK_LAUNCH(ctx, "k_leaf_init");
+    if (T == 1) {
+        k_single_leaf_root<<<1, 1, 0, stream>>>(leaf_lo, leaf_hi, ctx->nodes, meta);
+        LRC_CHECK_LAUNCH(ctx, "k_single_leaf_root");
+    } else {
+        const unsigned gN = (unsigned)((T - 1 + TB - 1) / TB);
+        k_hierarchy<<<gN, TB, 0, stream>>>(kin, (int)T, children, parent_node, parent_leaf);
+        LRC_CHECK_LAUNCH(ctx, "k_hierarchy");
+        LRC_CUDA(ctx, cudaMemsetAsync(flags, 0, sizeof(int) * n_nodes, stream));
+        k_refit<<<gT, TB, 0, stream>>>((int)T, parent_leaf, parent_node, children, leaf_lo, leaf_hi, node_lo, node_hi, flags,
+                                       ctx->nodes, meta);
+        LRC_CHECK_LAUNCH(ctx, "k_refit");
+    }
+    LRC_CUDA(ctx, cudaMemcpyAsync(&hm, meta, sizeof hm, cudaMemcpyDeviceToHost, stream));
+    LRC_CUDA(ctx, cudaStreamSynchronize(stream));
+
+    lrc_bvh_info& inf = ctx->info;
+    inf.num_tris = T;
+    inf.num_nodes = n_nodes;
+    inf.max_depth = hm.height;
+    for (int k = 0; k < 3; ++k) { inf.scene_min[k] = slo[k]; inf.scene_max[k] = shi[k]; }
+    inf.box_pad = pad;
+    {
+        float ex = hm.root_hi[0] - hm.root_lo[0], ey = hm.root_hi[1] - hm.root_lo[1], ez = hm.root_hi[2] - hm.root_lo[2];
+        double root_area = 2.0 * ((double)ex * ey + (double)ey * ez + (double)ez * ex);
+        inf.sah_cost = root_area > 0 ? (float)(hm.area_sum / root_area) : 0.f;
+    }
+    inf.bytes_nodes = (int64_t)sizeof(float4) * 4 * n_nodes;
+    inf.bytes_tris = (int64_t)sizeof(float4) * 3 * T;
+    if (hm.height + 1 >= LRC_STACK_DEPTH) {
+        char buf[32];
+        snprintf(buf, sizeof buf, "%d", hm.height);
+        return lrc_fail(ctx, LRC_ERR_CAPACITY, "lrc_set_mesh: BVH height %s exceeds the traversal stack (degenerate mesh?)", buf);
+    }
+    ctx->has_mesh = true;
+    return LRC_OK;
+}
+
+extern "C" int lrc_bvh_get_info(lrc_ctx* ctx, lrc_bvh_info* h_info)
+{
+    if (!ctx || !h_info) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_bvh_get_info: NULL argument");
+    if (!ctx->has_mesh) return lrc_fail(ctx, LRC_ERR_NO_MESH, "lrc_bvh_get_info: no mesh set");
+    *h_info = ctx->info;
+    return LRC_OK;
+}

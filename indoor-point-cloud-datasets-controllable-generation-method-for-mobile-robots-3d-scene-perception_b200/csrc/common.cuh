@@ -1,0 +1,111 @@
+// common.cuh -- context, error plumbing and small device helpers shared by the engine's kernels.
+// Target: sm_100a only (B200).  No CPU fallback exists anywhere in this library.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/lrc.h"
+
+#define LRC_STACK_DEPTH 64        // per-ray traversal stack entries (checked against the built tree)
+#define LRC_MAX_H 4096            // scan lines per single-axis sensor
+
+struct lrc_ctx {
+    int device = 0;
+    char err[512] = {0};
+    int64_t launches = 0;
+
+    // ---- scene (owned) ----
+    bool has_mesh = false;
+    bool has_labels = false;
+    int64_t T = 0, V = 0;
+    float4* nodes = nullptr;      // num_nodes x 4 float4 (64 B records)
+    float4* tris = nullptr;       // T x 3 float4 (48 B records, Morton order): (v0|orig id) (e1|0) (e2|0)
+    uint32_t* labels = nullptr;   // T, original triangle order
+    size_t nodes_cap = 0, tris_cap = 0, labels_cap = 0;   // in elements
+    lrc_bvh_info info = {};
+
+    // ---- grow-only scratch ----
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    void* scratch2 = nullptr;     // scan bookkeeping (tile status words, ticket, running total)
+    size_t scratch2_bytes = 0;
+    double* tables = nullptr;     // ray-generation tables
+    size_t tables_bytes = 0;
+
+    // ---- measurement ----
+    unsigned long long* d_counters = nullptr;   // rays, nodes, tris, hits
+    int counting = 0;
+
+    // ---- options ----
+    int64_t opt_block = 128;            // threads per traversal block
+    int64_t opt_chunk_rays = 1 << 26;   // rays per traversal/epilogue chunk (bounds scratch: 16 B per ray)
+    int64_t opt_variant = 0;            // traversal kernel variant
+};
+
+extern char g_lrc_global_err[512];
+
+static inline int lrc_fail(lrc_ctx* ctx, int code, const char* fmt, const char* a = "", const char* b = "")
+{
+    char* dst = ctx ? ctx->err : g_lrc_global_err;
+    snprintf(dst, 512, fmt, a, b);
+    return code;
+}
+
+#define LRC_CUDA(ctx, call)                                                                      \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess) return lrc_fail(ctx, LRC_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+#define LRC_CHECK_LAUNCH(ctx, name)                                                              \
+    do {                                                                                         \
+        (ctx)->launches++;                                                                       \
+        cudaError_t e__ = cudaGetLastError();                                                    \
+        if (e__ != cudaSuccess) return lrc_fail(ctx, LRC_ERR_CUDA, "launch %s: %s", name, cudaGetErrorString(e__)); \
+    } while (0)
+
+static inline int lrc_grow(lrc_ctx* ctx, void** p, size_t* cap_bytes, size_t need_bytes)
+{
+    if (*cap_bytes >= need_bytes && *p) return LRC_OK;
+    if (*p) { LRC_CUDA(ctx, cudaFree(*p)); *p = nullptr; *cap_bytes = 0; }
+    size_t n = need_bytes < 256 ? 256 : need_bytes;
+    LRC_CUDA(ctx, cudaMalloc(p, n));
+    *cap_bytes = n;
+    return LRC_OK;
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- device helpers -----------------------------------------------------------------------------
+#define LRC_INF __int_as_float(0x7f800000)
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+
+// order-preserving float <-> uint mapping for atomicMin/atomicMax on floats
+__device__ __forceinline__ unsigned f2ord(float f)
+{
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u)
+{
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// Philox4x32-10 (Salmon et al. SC'11).  key = seed, counter = (ray, pose_lo, pose_hi, stream).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ double u01(uint32_t r) { return ((double)r + 0.5) * (1.0 / 4294967296.0); }

@@ -1,0 +1,702 @@
+// scan.cu -- ray generation, traversal launches and the fused epilogue (label gather + range filter +
+// incident angle + ordered compaction).  Together these replace, per waypoint,
+//     RaycastEngineCPU.lidar_intersect_mesh / rays_intersect_mesh  (reference raycast_engine_cpu.py:24-111)
+// and IndoorLidar.get_rays / DualAxisLidar.get_rays                 (reference indoor_lidar.py:27-131,224-319).
+#include "traverse.cuh"
+
+char g_lrc_global_err[512] = {0};
+
+namespace {
+
+constexpr double PI_D = 3.141592653589793;
+constexpr int EPI_THREADS = 256;
+constexpr int EPI_ITEMS = 4;
+constexpr int EPI_TILE = EPI_THREADS * EPI_ITEMS;
+constexpr unsigned long long ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_MASK = (1ull << 62) - 1;
+
+enum { MODE_SINGLE = 0, MODE_DUAL = 1, MODE_RAYS = 2 };
+
+struct RayGen {
+    // common
+    const double* poses;       // P x 16, row-major 4x4
+    int64_t pose0;             // first pose of this launch (index into poses)
+    int N;                     // rays per frame (dense, before dropout)
+    int W;                     // single: horizontal_res ; dual: points_per_line
+    int H;                     // single: lines ; dual: num_lines
+    // single axis: tables [cos beta | sin beta | cos alpha | sin alpha] (float64)
+    const double* tab;
+    int uniform_mode;          // 1: round the local direction to float32 before rotating (indoor_lidar.py:82)
+    // dual axis
+    double theta_min, theta_max, tstep, pstep, swing_amp, swing_freq;
+    // noise
+    double angle_std, dropout_p, range_std;
+    uint32_t k0, k1;
+    uint64_t pose_index_base;
+    // explicit rays
+    const float* rays;
+};
+
+struct Ray { float ox, oy, oz, dx, dy, dz; bool keep; };
+
+__device__ __forceinline__ void rotate(const double* __restrict__ M, double lx, double ly, double lz, Ray& r)
+{
+    // world = R . local ; origin = pose[:3,3] ; float64 math, a single rounding to float32
+    r.dx = (float)(M[0] * lx + M[1] * ly + M[2] * lz);
+    r.dy = (float)(M[4] * lx + M[5] * ly + M[6] * lz);
+    r.dz = (float)(M[8] * lx + M[9] * ly + M[10] * lz);
+    r.ox = (float)M[3];
+    r.oy = (float)M[7];
+    r.oz = (float)M[11];
+}
+
+// ray index inside a frame = j*W + i (line-major, azimuth-minor): reference indoor_lidar.py:108-110
+__device__ __forceinline__ Ray gen_single(const RayGen& g, int64_t pose, int r)
+{
+    const int j = r / g.W, i = r - j * g.W;
+    const double cb = g.tab[i], sb = g.tab[g.W + i], ca = g.tab[2 * g.W + j], sa = g.tab[2 * g.W + g.H + j];
+    double lx = ca * cb, ly = ca * sb, lz = sa;
+    if (g.uniform_mode) { lx = (double)(float)lx; ly = (double)(float)ly; lz = (double)(float)lz; }
+    Ray out;
+    rotate(g.poses + 16 * (g.pose0 + pose), lx, ly, lz, out);
+    out.keep = true;
+    return out;
+}
+
+// reference indoor_lidar.py:247-294
+__device__ __forceinline__ Ray gen_dual(const RayGen& g, int64_t pose, int r)
+{
+    const int line = r / g.W, k = r - line * g.W;
+    const double base = (g.H > 1 && line == g.H - 1) ? g.theta_min : g.theta_max + (double)line * g.tstep;
+    const double phase = (double)line * PI_D / (double)g.H;
+    double phi = (double)k * g.pstep;
+    double theta = base + g.swing_amp * sin(g.swing_freq * phi + phase);
+    theta = fmin(fmax(theta, g.theta_min), g.theta_max);
+    Ray out;
+    out.keep = true;
+    if (g.angle_std > 0.0 || g.dropout_p > 0.0) {
+        const uint64_t pidx = g.pose_index_base + (uint64_t)(g.pose0 + pose);
+        const uint4 rnd = philox4x32_10(make_uint4((uint32_t)r, (uint32_t)pidx, (uint32_t)(pidx >> 32), 0u), g.k0, g.k1);
+        if (g.angle_std > 0.0) {   // Box-Muller; noise is added AFTER the clip (indoor_lidar.py:267-272)
+            const double rad = sqrt(-2.0 * log(u01(rnd.x)));
+            double sn, cs;
+            sincos(2.0 * PI_D * u01(rnd.y), &sn, &cs);
+            phi += g.angle_std * (rad * cs);
+            theta += g.angle_std * (rad * sn);
+        }
+        if (g.dropout_p > 0.0) out.keep = u01(rnd.z) > g.dropout_p;   // indoor_lidar.py:292-294
+    }
+    double st, ct, sp, cp;
+    sincos(theta, &st, &ct);
+    sincos(phi, &sp, &cp);
+    rotate(g.poses + 16 * (g.pose0 + pose), ct * cp, ct * sp, st, out);
+    return out;
+}
+
+__device__ __forceinline__ Ray gen_explicit(const RayGen& g, int64_t idx)
+{
+    const float2* p = reinterpret_cast<const float2*>(g.rays + 6 * idx);
+    const float2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    Ray out;
+    out.ox = a.x; out.oy = a.y; out.oz = b.x;
+    out.dx = b.y; out.dy = c.x; out.dz = c.y;
+    out.keep = true;
+    return out;
+}
+
+template <int MODE>
+__device__ __forceinline__ Ray gen_ray(const RayGen& g, int64_t idx, int64_t& pose, int& r)
+{
+    if (MODE == MODE_RAYS) { pose = 0; r = (int)idx; return gen_explicit(g, idx); }
+    pose = idx / g.N;
+    r = (int)(idx - pose * g.N);
+    return MODE == MODE_SINGLE ? gen_single(g, pose, r) : gen_dual(g, pose, r);
+}
+
+// standard normal for the range noise: Philox stream 1 of the same (seed, pose, ray) counter
+__device__ __forceinline__ double range_normal(const RayGen& g, int64_t pose, int r)
+{
+    const uint64_t pidx = g.pose_index_base + (uint64_t)(g.pose0 + pose);
+    const uint4 rnd = philox4x32_10(make_uint4((uint32_t)r, (uint32_t)pidx, (uint32_t)(pidx >> 32), 1u), g.k0, g.k1);
+    return sqrt(-2.0 * log(u01(rnd.x))) * cos(2.0 * PI_D * u01(rnd.y));
+}
+
+// ---- table kernel: cos/sin of azimuth and elevation in float64 ---------------------------------------
+// beta = -(i - W/2)/W*2*pi (indoor_lidar.py:113), alpha = deg2rad(v[j]) (:116); uniform mode: linspace tables (:66-72)
+__global__ void k_single_tables(double* tab, int W, int H, const double* vdeg, int uniform_mode, double fov_up_deg,
+                                double fov_down_deg)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < W) {
+        double beta;
+        if (uniform_mode) beta = (double)t * ((2.0 * PI_D - 0.0) / (double)W);
+        else beta = -((double)t - (double)W / 2.0) / (double)W * 2.0 * PI_D;
+        tab[t] = cos(beta);
+        tab[W + t] = sin(beta);
+    } else if (t < W + H) {
+        int j = t - W;
+        double alpha;
+        if (uniform_mode) {
+            double up = fov_up_deg * (PI_D / 180.0), dn = fov_down_deg * (PI_D / 180.0);
+            double step = H > 1 ? ((-dn) - up) / (double)(H - 1) : 0.0;
+            alpha = (H > 1 && j == H - 1) ? -dn : up + (double)j * step;
+        } else alpha = vdeg[j] * (PI_D / 180.0);
+        tab[2 * W + j] = cos(alpha);
+        tab[2 * W + H + j] = sin(alpha);
+    }
+}
+
+// ---- ray table export (get_rays) ---------------------------------------------------------------------
+template <int MODE>
+__global__ void k_gen_rays(RayGen g, int64_t n, float* __restrict__ rays, uint8_t* __restrict__ keep)
+{
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    int64_t pose; int r;
+    Ray ray = gen_ray<MODE>(g, idx, pose, r);
+    float2* o = reinterpret_cast<float2*>(rays + 6 * idx);
+    o[0] = make_float2(ray.ox, ray.oy);
+    o[1] = make_float2(ray.oz, ray.dx);
+    o[2] = make_float2(ray.dy, ray.dz);
+    if (keep) keep[idx] = ray.keep ? 1 : 0;
+}
+
+// ---- traversal kernels -------------------------------------------------------------------------------
+// OUT_DENSE: write (t_hit, prim_id) per ray (cast_rays).  Otherwise write the float32 hit point and the
+// triangle id as one float4 per ray for the epilogue:
+//     d^ = d / sqrt((dx*dx + dy*dy) + dz*dz) ; p = o + d^ * t      (raycast_engine_cpu.py:57,62; separate roundings)
+template <int MODE, bool COUNT, bool OUT_DENSE>
+__global__ void __launch_bounds__(128)
+k_trace(RayGen g, const float4* __restrict__ nodes, const float4* __restrict__ tris, int64_t n, int has_tris,
+        float4* __restrict__ hp, float* __restrict__ t_hit, uint32_t* __restrict__ prim_id, unsigned long long* counters)
+{
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned nn = 0, nt = 0, nr = 0, nh = 0;
+    if (idx < n) {
+        int64_t pose; int r;
+        Ray ray = gen_ray<MODE>(g, idx, pose, r);
+        float t = LRC_INF;
+        uint32_t id = LRC_MISS_ID;
+        if (ray.keep && has_tris) {
+            trace_ray<COUNT>(nodes, tris, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, t, id, nn, nt);
+            nr = 1;
+            nh = id != LRC_MISS_ID;
+        }
+        if (OUT_DENSE) {
+            t_hit[idx] = t;
+            prim_id[idx] = id;
+        } else {
+            float4 o = make_float4(0.f, 0.f, 0.f, __uint_as_float(LRC_MISS_ID));
+            if (id != LRC_MISS_ID) {
+                if (g.range_std > 0.0) t = __fadd_rn(t, (float)(g.range_std * range_normal(g, pose, r)));
+                float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ray.dx, ray.dx), __fmul_rn(ray.dy, ray.dy)), __fmul_rn(ray.dz, ray.dz)));
+                o.x = __fadd_rn(ray.ox, __fmul_rn(__fdiv_rn(ray.dx, nrm), t));
+                o.y = __fadd_rn(ray.oy, __fmul_rn(__fdiv_rn(ray.dy, nrm), t));
+                o.z = __fadd_rn(ray.oz, __fmul_rn(__fdiv_rn(ray.dz, nrm), t));
+                o.w = __uint_as_float(id);
+            }
+            hp[idx] = o;
+        }
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            nn += __shfl_xor_sync(0xffffffffu, nn, o);
+            nt += __shfl_xor_sync(0xffffffffu, nt, o);
+            nr += __shfl_xor_sync(0xffffffffu, nr, o);
+            nh += __shfl_xor_sync(0xffffffffu, nh, o);
+        }
+        if (lane_id() == 0) {
+            atomicAdd(&counters[0], (unsigned long long)nr);
+            atomicAdd(&counters[1], (unsigned long long)nn);
+            atomicAdd(&counters[2], (unsigned long long)nt);
+            atomicAdd(&counters[3], (unsigned long long)nh);
+        }
+    }
+}
+
+// exhaustive validation kernel: every ray against every triangle record
+__global__ void k_brute(const float* __restrict__ rays, int64_t n, const float4* __restrict__ tris, int64_t T,
+                        float* __restrict__ t_hit, uint32_t* __restrict__ prim_id)
+{
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const float* p = rays + 6 * idx;
+    float ox = p[0], oy = p[1], oz = p[2], dx = p[3], dy = p[4], dz = p[5];
+    float best_t = LRC_INF;
+    uint32_t best_id = LRC_MISS_ID;
+    for (int64_t s = 0; s < T; ++s) {
+        float4 v0 = __ldg(tris + 3 * s), e1 = __ldg(tris + 3 * s + 1), e2 = __ldg(tris + 3 * s + 2);
+        float t;
+        if (mt_hit(ox, oy, oz, dx, dy, dz, v0, e1, e2, t)) {
+            uint32_t id = __float_as_uint(v0.w);
+            if (t < best_t || (t == best_t && id < best_id)) { best_t = t; best_id = id; }
+        }
+    }
+    t_hit[idx] = best_t;
+    prim_id[idx] = best_id;
+}
+
+// ---- fused epilogue ----------------------------------------------------------------------------------
+// Per ray: range filter on the float64 distance recomputed from the float32 point with strict '<'
+// (raycast_engine_cpu.py:95-97), incident = degrees(arccos(|dz/dist|)) (:100-107), label gather by triangle
+// id, and ORDER-PRESERVING compaction (the reference's boolean-mask indexing keeps ray order, :71,:97):
+// thread-local counts -> warp shuffle scan -> block scan -> single-pass chained scan across tiles with
+// decoupled look-back (tiles take tickets so that every predecessor is already resident).
+struct EpiParams {
+    const float4* hp;
+    int64_t n;                 // rays in this launch
+    int64_t ray0;              // global index of the first ray of this launch
+    int64_t N;                 // rays per frame
+    int64_t P;                 // total frames of the whole call
+    const double* poses;       // frame centres come from here ...
+    double cx, cy, cz;         // ... or from here when poses == NULL
+    double max_range;          // < 0: no range filter, no incident angle (rays_intersect_mesh)
+    const uint32_t* labels;
+    lrc_out out;
+    unsigned long long* status;
+    unsigned* ticket;
+    const long long* run_in;   // points already emitted by earlier launches of this call
+    long long* run_out;
+    int last;                  // this launch finishes the call: write frame_offset[P]
+};
+
+__global__ void __launch_bounds__(EPI_THREADS) k_epilogue(EpiParams q)
+{
+    __shared__ unsigned s_tile;
+    __shared__ int s_warp[EPI_THREADS / 32];
+    __shared__ long long s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(q.ticket, 1u);
+    __syncthreads();
+    const int64_t tile = s_tile;
+    const int64_t first = tile * EPI_TILE + (int64_t)threadIdx.x * EPI_ITEMS;
+
+    float4 h[EPI_ITEMS];
+    double inc[EPI_ITEMS];
+    bool keep[EPI_ITEMS];
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < EPI_ITEMS; ++k) {
+        const int64_t i = first + k;
+        keep[k] = false;
+        inc[k] = 0.0;
+        if (i < q.n) {
+            h[k] = __ldcs(q.hp + i);
+            if (__float_as_uint(h[k].w) != LRC_MISS_ID) {
+                keep[k] = true;
+                if (q.max_range >= 0.0) {
+                    double cx = q.cx, cy = q.cy, cz = q.cz;
+                    if (q.poses) {
+                        const double* M = q.poses + 16 * ((q.ray0 + i) / q.N);
+                        cx = M[3]; cy = M[7]; cz = M[11];
+                    }
+                    const double ddx = __dsub_rn((double)h[k].x, cx), ddy = __dsub_rn((double)h[k].y, cy),
+                                 ddz = __dsub_rn((double)h[k].z, cz);
+                    const double dist = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz)));
+                    keep[k] = dist < q.max_range;
+                    inc[k] = __dmul_rn(acos(fabs(__ddiv_rn(ddz, dist))), 180.0 / PI_D);
+                }
+            }
+        }
+        cnt += keep[k] ? 1 : 0;
+    }
+    // block-level exclusive scan of per-thread counts
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    int warp_off = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < EPI_THREADS / 32; ++k) {
+        int v = s_warp[k];
+        if (k < w) warp_off += v;
+        total += v;
+    }
+    const int local_excl = warp_off + incl - cnt;
+
+    // chained scan across tiles (decoupled look-back), warp 0 only
+    if (w == 0) {
+        long long excl = 0;
+        if (tile > 0) {
+            if (lane == 0) {
+                *((volatile unsigned long long*)&q.status[tile]) = ST_AGG | (unsigned long long)total;
+            }
+            int64_t look = tile - 1;
+            for (;;) {
+                const int64_t j = look - lane;
+                unsigned long long s = ST_INC;   // virtual "inclusive 0" in front of tile 0
+                if (j >= 0) {
+                    do { s = *((volatile unsigned long long*)&q.status[j]); } while ((s >> 62) == 0ull);
+                }
+                const unsigned inc_mask = __ballot_sync(0xffffffffu, (s >> 62) == 2ull);
+                long long v = (long long)(s & ST_MASK);
+                if (inc_mask) {
+                    const int stop = __ffs(inc_mask) - 1;   // nearest predecessor holding an inclusive prefix
+                    if (lane > stop) v = 0;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                excl += v;
+                if (inc_mask) break;
+                look -= 32;
+            }
+        }
+        if (lane == 0) {
+            *((volatile unsigned long long*)&q.status[tile]) = ST_INC | (unsigned long long)(excl + total);
+            s_prefix = excl;
+        }
+    }
+    __syncthreads();
+    const long long run0 = *q.run_in;
+    long long pos = run0 + s_prefix + local_excl;
+#pragma unroll
+    for (int k = 0; k < EPI_ITEMS; ++k) {
+        const int64_t i = first + k;
+        if (i < q.n) {
+            const int64_t gidx = q.ray0 + i;
+            const int64_t frame = gidx / q.N;
+            const int64_t r = gidx - frame * q.N;
+            if (r == 0) q.out.frame_offset[frame] = pos;
+            if (keep[k]) {
+                if (pos < q.out.capacity) {
+                    const uint32_t id = __float_as_uint(h[k].w);
+                    q.out.xyz[3 * pos + 0] = h[k].x;
+                    q.out.xyz[3 * pos + 1] = h[k].y;
+                    q.out.xyz[3 * pos + 2] = h[k].z;
+                    if (q.out.incident_deg) q.out.incident_deg[pos] = inc[k];
+                    if (q.out.prim_id) q.out.prim_id[pos] = id;
+                    if (q.out.label) q.out.label[pos] = __ldg(q.labels + id);
+                    if (q.out.ray_idx) q.out.ray_idx[pos] = (uint32_t)r;
+                }
+                ++pos;
+            }
+        }
+    }
+    // the tile that owns the last ray of this launch closes the books
+    if (first <= q.n - 1 && q.n - 1 < first + EPI_ITEMS) {
+        *q.run_out = pos;
+        if (q.last) q.out.frame_offset[q.P] = pos;
+    }
+}
+
+// ---- host-side launch plumbing -----------------------------------------------------------------------
+int ensure_counters(lrc_ctx* ctx)
+{
+    if (!ctx->d_counters) {
+        LRC_CUDA(ctx, cudaMalloc((void**)&ctx->d_counters, 4 * sizeof(unsigned long long)));
+        LRC_CUDA(ctx, cudaMemset(ctx->d_counters, 0, 4 * sizeof(unsigned long long)));
+    }
+    return LRC_OK;
+}
+
+template <int MODE, bool DENSE>
+int launch_trace(lrc_ctx* ctx, const RayGen& g, int64_t n, float4* hp, float* t_hit, uint32_t* prim, cudaStream_t stream)
+{
+    if (n <= 0) return LRC_OK;
+    const int TB = 128;
+    const unsigned grid = (unsigned)((n + TB - 1) / TB);
+    const int has_tris = ctx->T > 0;
+    if (ctx->counting) {
+        k_trace<MODE, true, DENSE><<<grid, TB, 0, stream>>>(g, ctx->nodes, ctx->tris, n, has_tris, hp, t_hit, prim, ctx->d_counters);
+    } else {
+        k_trace<MODE, false, DENSE><<<grid, TB, 0, stream>>>(g, ctx->nodes, ctx->tris, n, has_tris, hp, t_hit, prim, ctx->d_counters);
+    }
+    LRC_CHECK_LAUNCH(ctx, "k_trace");
+    return LRC_OK;
+}
+
+int check_out(lrc_ctx* ctx, const lrc_out* out, int64_t need)
+{
+    if (!out || !out->xyz || !out->frame_offset) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_out: xyz and frame_offset are required");
+    if (out->capacity < need) return lrc_fail(ctx, LRC_ERR_CAPACITY, "lrc_out: capacity is smaller than the number of rays");
+    return LRC_OK;
+}
+
+// Shared driver of all scan-type entry points: chunked trace -> epilogue with a running output offset.
+template <int MODE>
+int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* poses_for_center, const double* h_center,
+             double max_range, lrc_out* out, cudaStream_t stream)
+{
+    const int64_t total = P * N;
+    int rc = check_out(ctx, out, total);
+    if (rc) return rc;
+    if ((rc = ensure_counters(ctx))) return rc;
+    if (total == 0) {
+        LRC_CUDA(ctx, cudaMemsetAsync(out->frame_offset, 0, sizeof(int64_t) * (P + 1), stream));
+        return LRC_OK;
+    }
+    // chunk by whole frames where possible so scratch stays bounded (16 B per ray)
+    int64_t frames_per_chunk = ctx->opt_chunk_rays / N;
+    if (frames_per_chunk < 1) frames_per_chunk = 1;
+    if (MODE == MODE_RAYS) frames_per_chunk = P;   // a single explicit frame
+    const int64_t n_chunks = (P + frames_per_chunk - 1) / frames_per_chunk;
+    const int64_t chunk_rays = frames_per_chunk * N;
+    const int64_t max_tiles = (chunk_rays + EPI_TILE - 1) / EPI_TILE;
+    if ((rc = lrc_grow(ctx, &ctx->scratch, &ctx->scratch_bytes, sizeof(float4) * (size_t)chunk_rays))) return rc;
+    const size_t st_bytes = align_up(sizeof(unsigned long long) * (size_t)max_tiles, 256);
+    const size_t need2 = st_bytes * 2 + 256 + sizeof(long long) * (size_t)(n_chunks + 1);
+    if ((rc = lrc_grow(ctx, &ctx->scratch2, &ctx->scratch2_bytes, need2))) return rc;
+    char* b2 = (char*)ctx->scratch2;
+    long long* run = (long long*)(b2 + 2 * st_bytes + 256);
+    LRC_CUDA(ctx, cudaMemsetAsync(run, 0, sizeof(long long), stream));
+    float4* hp = (float4*)ctx->scratch;
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        const int64_t f0 = c * frames_per_chunk;
+        const int64_t nf = (f0 + frames_per_chunk <= P) ? frames_per_chunk : P - f0;
+        const int64_t n = nf * N;
+        g.pose0 = f0;
+        if ((rc = launch_trace<MODE, false>(ctx, g, n, hp, nullptr, nullptr, stream))) return rc;
+        unsigned long long* status = (unsigned long long*)(b2 + (c & 1) * st_bytes);
+        unsigned* ticket = (unsigned*)(b2 + 2 * st_bytes + 64 * (c & 1));
+        const int64_t tiles = (n + EPI_TILE - 1) / EPI_TILE;
+        LRC_CUDA(ctx, cudaMemsetAsync(status, 0, sizeof(unsigned long long) * tiles, stream));
+        LRC_CUDA(ctx, cudaMemsetAsync(ticket, 0, sizeof(unsigned), stream));
+        EpiParams q;
+        q.hp = hp; q.n = n; q.ray0 = f0 * N; q.N = N; q.P = P;
+        q.poses = poses_for_center;
+        q.cx = h_center ? h_center[0] : 0.0; q.cy = h_center ? h_center[1] : 0.0; q.cz = h_center ? h_center[2] : 0.0;
+        q.max_range = max_range;
+        q.labels = ctx->labels;
+        q.out = *out;
+        if (ctx->T == 0) q.out.label = nullptr;
+        q.status = status; q.ticket = ticket;
+        q.run_in = run + c; q.run_out = run + c + 1;
+        q.last = (c == n_chunks - 1);
+        k_epilogue<<<(unsigned)tiles, EPI_THREADS, 0, stream>>>(q);
+        LRC_CHECK_LAUNCH(ctx, "k_epilogue");
+    }
+    return LRC_OK;
+}
+
+int fill_single(lrc_ctx* ctx, const lrc_single_axis* s, const double* poses, RayGen& g, cudaStream_t stream)
+{
+    if (!s || s->H < 1 || s->W < 1 || s->H > LRC_MAX_H) return lrc_fail(ctx, LRC_ERR_INVALID, "single-axis sensor: need 1 <= H <= 4096 and W >= 1");
+    if ((int64_t)s->H * s->W >= (int64_t)1 << 31) return lrc_fail(ctx, LRC_ERR_INVALID, "single-axis sensor: H*W must be < 2^31");
+    memset(&g, 0, sizeof g);
+    g.poses = poses;
+    g.H = s->H; g.W = s->W; g.N = s->H * s->W;
+    g.uniform_mode = s->h_vertical_deg ? 0 : 1;
+    const size_t n_tab = (size_t)2 * s->W + 2 * s->H;
+    int rc = lrc_grow(ctx, (void**)&ctx->tables, &ctx->tables_bytes, sizeof(double) * (n_tab + s->H));
+    if (rc) return rc;
+    double* vdeg = ctx->tables + n_tab;
+    if (s->h_vertical_deg)
+        LRC_CUDA(ctx, cudaMemcpyAsync(vdeg, s->h_vertical_deg, sizeof(double) * s->H, cudaMemcpyHostToDevice, stream));
+    const int n = s->W + s->H;
+    k_single_tables<<<(n + 255) / 256, 256, 0, stream>>>(ctx->tables, s->W, s->H, vdeg, g.uniform_mode, s->fov_up_deg, s->fov_down_deg);
+    LRC_CHECK_LAUNCH(ctx, "k_single_tables");
+    g.tab = ctx->tables;
+    return LRC_OK;
+}
+
+int fill_dual(lrc_ctx* ctx, const lrc_dual_axis* s, const double* poses, RayGen& g)
+{
+    if (!s || s->num_lines < 1 || s->points_per_line < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "dual-axis sensor: need num_lines >= 1 and points_per_line >= 1");
+    if ((int64_t)s->num_lines * s->points_per_line >= (int64_t)1 << 31) return lrc_fail(ctx, LRC_ERR_INVALID, "dual-axis sensor: too many rays per frame");
+    memset(&g, 0, sizeof g);
+    g.poses = poses;
+    g.H = s->num_lines; g.W = s->points_per_line; g.N = s->num_lines * s->points_per_line;
+    g.theta_min = s->theta_min; g.theta_max = s->theta_max;
+    g.tstep = s->num_lines > 1 ? (s->theta_min - s->theta_max) / (double)(s->num_lines - 1) : 0.0;   // linspace(theta_max, theta_min, L)
+    g.pstep = (2.0 * PI_D - 0.0) / (double)s->points_per_line;                                         // linspace(0, 2pi, K, endpoint=False)
+    g.swing_amp = s->swing_amplitude; g.swing_freq = s->swing_frequency;
+    return LRC_OK;
+}
+
+void fill_noise(const lrc_noise* nz, RayGen& g, bool dual)
+{
+    if (!nz) return;
+    if (dual) { g.angle_std = nz->angle_noise_std; g.dropout_p = nz->dropout_probability; }
+    g.range_std = nz->range_noise_std;
+    g.k0 = (uint32_t)nz->seed; g.k1 = (uint32_t)(nz->seed >> 32);
+    g.pose_index_base = nz->pose_index_base;
+}
+
+int precheck(lrc_ctx* ctx, const char* who)
+{
+    if (!ctx) return lrc_fail(nullptr, LRC_ERR_INVALID, "%s: ctx is NULL", who);
+    if (!ctx->has_mesh) return lrc_fail(ctx, LRC_ERR_NO_MESH, "%s: call lrc_set_mesh first", who);
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return lrc_fail(ctx, LRC_ERR_CUDA, "%s: cudaSetDevice: %s", who, cudaGetErrorString(e));
+    return LRC_OK;
+}
+
+}  // namespace
+
+// ======================================================================================================
+extern "C" int lrc_abi_version(void) { return LRC_ABI_VERSION; }
+
+extern "C" int lrc_create(int device, lrc_ctx** out)
+{
+    if (!out) return lrc_fail(nullptr, LRC_ERR_INVALID, "lrc_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return lrc_fail(nullptr, LRC_ERR_NO_DEVICE, "lrc_create: no CUDA device (%s); this engine has no CPU fallback",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n) return lrc_fail(nullptr, LRC_ERR_INVALID, "lrc_create: device index out of range");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return lrc_fail(nullptr, LRC_ERR_CUDA, "lrc_create: cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return lrc_fail(nullptr, LRC_ERR_NO_DEVICE, "lrc_create: device '%s' is not sm_100 (this library is built for B200 only)", prop.name);
+    if ((e = cudaSetDevice(device)) != cudaSuccess)
+        return lrc_fail(nullptr, LRC_ERR_CUDA, "lrc_create: cudaSetDevice: %s", cudaGetErrorString(e));
+    lrc_ctx* ctx = new lrc_ctx();
+    ctx->device = device;
+    *out = ctx;
+    return LRC_OK;
+}
+
+extern "C" void lrc_destroy(lrc_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->nodes); cudaFree(ctx->tris); cudaFree(ctx->labels);
+    cudaFree(ctx->scratch); cudaFree(ctx->scratch2); cudaFree(ctx->tables); cudaFree(ctx->d_counters);
+    delete ctx;
+}
+
+extern "C" const char* lrc_last_error(const lrc_ctx* ctx) { return ctx ? ctx->err : g_lrc_global_err; }
+
+extern "C" int64_t lrc_launch_count(const lrc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int lrc_set_counting(lrc_ctx* ctx, int enabled)
+{
+    if (!ctx) return lrc_fail(nullptr, LRC_ERR_INVALID, "lrc_set_counting: ctx is NULL");
+    ctx->counting = enabled ? 1 : 0;
+    return ensure_counters(ctx);
+}
+
+extern "C" int lrc_counters(lrc_ctx* ctx, lrc_counters_t* h_out, int reset, void* stream_)
+{
+    if (!ctx || !h_out) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_counters: NULL argument");
+    int rc = ensure_counters(ctx);
+    if (rc) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    unsigned long long h[4];
+    LRC_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost, stream));
+    if (reset) LRC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof h, stream));
+    LRC_CUDA(ctx, cudaStreamSynchronize(stream));
+    h_out->rays = h[0]; h_out->nodes_visited = h[1]; h_out->tris_tested = h[2]; h_out->hits = h[3];
+    return LRC_OK;
+}
+
+extern "C" int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value)
+{
+    if (!ctx || !key) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_option: NULL argument");
+    if (!strcmp(key, "chunk_rays")) { if (value < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "chunk_rays must be >= 1"); ctx->opt_chunk_rays = value; return LRC_OK; }
+    if (!strcmp(key, "variant")) { ctx->opt_variant = value; return LRC_OK; }
+    return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_option: unknown key '%s'", key);
+}
+
+extern "C" int lrc_cast_rays(lrc_ctx* ctx, const float* rays, int64_t N, float* t_hit, uint32_t* prim_id, void* stream)
+{
+    int rc = precheck(ctx, "lrc_cast_rays");
+    if (rc) return rc;
+    if (N < 0 || (N > 0 && (!rays || !t_hit || !prim_id))) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_cast_rays: bad arguments");
+    if ((rc = ensure_counters(ctx))) return rc;
+    RayGen g;
+    memset(&g, 0, sizeof g);
+    g.rays = rays; g.N = 1;
+    return launch_trace<MODE_RAYS, true>(ctx, g, N, nullptr, t_hit, prim_id, (cudaStream_t)stream);
+}
+
+extern "C" int lrc_cast_rays_bruteforce(lrc_ctx* ctx, const float* rays, int64_t N, float* t_hit, uint32_t* prim_id, void* stream)
+{
+    int rc = precheck(ctx, "lrc_cast_rays_bruteforce");
+    if (rc) return rc;
+    if (N < 0 || (N > 0 && (!rays || !t_hit || !prim_id))) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_cast_rays_bruteforce: bad arguments");
+    if (N == 0) return LRC_OK;
+    k_brute<<<(unsigned)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(rays, N, ctx->tris, ctx->T, t_hit, prim_id);
+    LRC_CHECK_LAUNCH(ctx, "k_brute");
+    return LRC_OK;
+}
+
+extern "C" int lrc_rays_intersect(lrc_ctx* ctx, const float* rays, int64_t N, lrc_out* out, void* stream)
+{
+    int rc = precheck(ctx, "lrc_rays_intersect");
+    if (rc) return rc;
+    if (N < 0 || (N > 0 && !rays)) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_rays_intersect: bad arguments");
+    RayGen g;
+    memset(&g, 0, sizeof g);
+    g.rays = rays; g.N = (int)(N > 0 ? 1 : 0);
+    if (N >= (int64_t)1 << 31) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_rays_intersect: N must be < 2^31 per call");
+    // one frame of N rays
+    return run_scan<MODE_RAYS>(ctx, g, 1, N, nullptr, nullptr, -1.0, out, (cudaStream_t)stream);
+}
+
+extern "C" int lrc_scan_rays(lrc_ctx* ctx, const float* rays, int64_t N, const double* h_center, double max_range,
+                             lrc_out* out, void* stream)
+{
+    int rc = precheck(ctx, "lrc_scan_rays");
+    if (rc) return rc;
+    if (N < 0 || (N > 0 && !rays) || !h_center) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_scan_rays: bad arguments");
+    if (N >= (int64_t)1 << 31) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_scan_rays: N must be < 2^31 per call");
+    RayGen g;
+    memset(&g, 0, sizeof g);
+    g.rays = rays; g.N = 1;
+    return run_scan<MODE_RAYS>(ctx, g, 1, N, nullptr, h_center, max_range, out, (cudaStream_t)stream);
+}
+
+extern "C" int lrc_scan_single_axis(lrc_ctx* ctx, const double* poses, int64_t P, const lrc_single_axis* s,
+                                    const lrc_noise* nz, lrc_out* out, void* stream)
+{
+    int rc = precheck(ctx, "lrc_scan_single_axis");
+    if (rc) return rc;
+    if (P < 0 || (P > 0 && !poses)) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_scan_single_axis: bad poses");
+    RayGen g;
+    if ((rc = fill_single(ctx, s, poses, g, (cudaStream_t)stream))) return rc;
+    fill_noise(nz, g, false);
+    return run_scan<MODE_SINGLE>(ctx, g, P, g.N, poses, nullptr, s->max_range, out, (cudaStream_t)stream);
+}
+
+extern "C" int lrc_scan_dual_axis(lrc_ctx* ctx, const double* poses, int64_t P, const lrc_dual_axis* s,
+                                  const lrc_noise* nz, lrc_out* out, void* stream)
+{
+    int rc = precheck(ctx, "lrc_scan_dual_axis");
+    if (rc) return rc;
+    if (P < 0 || (P > 0 && !poses)) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_scan_dual_axis: bad poses");
+    RayGen g;
+    if ((rc = fill_dual(ctx, s, poses, g))) return rc;
+    fill_noise(nz, g, true);
+    return run_scan<MODE_DUAL>(ctx, g, P, g.N, poses, nullptr, s->max_range, out, (cudaStream_t)stream);
+}
+
+extern "C" int lrc_gen_rays_single_axis(lrc_ctx* ctx, const double* poses, int64_t P, const lrc_single_axis* s,
+                                        float* rays, void* stream)
+{
+    if (!ctx) return lrc_fail(nullptr, LRC_ERR_INVALID, "lrc_gen_rays_single_axis: ctx is NULL");
+    LRC_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (P < 0 || (P > 0 && (!poses || !rays))) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_gen_rays_single_axis: bad arguments");
+    RayGen g;
+    int rc = fill_single(ctx, s, poses, g, (cudaStream_t)stream);
+    if (rc) return rc;
+    const int64_t n = P * g.N;
+    if (n == 0) return LRC_OK;
+    k_gen_rays<MODE_SINGLE><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, n, rays, nullptr);
+    LRC_CHECK_LAUNCH(ctx, "k_gen_rays");
+    return LRC_OK;
+}
+
+extern "C" int lrc_gen_rays_dual_axis(lrc_ctx* ctx, const double* poses, int64_t P, const lrc_dual_axis* s,
+                                      const lrc_noise* nz, float* rays, uint8_t* keep, void* stream)
+{
+    if (!ctx) return lrc_fail(nullptr, LRC_ERR_INVALID, "lrc_gen_rays_dual_axis: ctx is NULL");
+    LRC_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (P < 0 || (P > 0 && (!poses || !rays))) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_gen_rays_dual_axis: bad arguments");
+    RayGen g;
+    int rc = fill_dual(ctx, s, poses, g);
+    if (rc) return rc;
+    fill_noise(nz, g, true);
+    const int64_t n = P * g.N;
+    if (n == 0) return LRC_OK;
+    k_gen_rays<MODE_DUAL><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, n, rays, keep);
+    LRC_CHECK_LAUNCH(ctx, "k_gen_rays");
+    return LRC_OK;
+}

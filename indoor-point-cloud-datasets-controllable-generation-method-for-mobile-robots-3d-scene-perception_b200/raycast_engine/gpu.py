@@ -1,0 +1,97 @@
+"""
+``RaycastEngineGPU`` -- the drop-in for the engine object ``S3DISSimulator`` holds
+(reference s3dis_simulator.py:67-74) and calls once per waypoint (:261).
+
+Same class name, constructor and two methods as the reference's
+``raycast_engine/raycast_engine_gpu_simple.py:12-98`` (which, despite its name, runs Open3D on the CPU);
+same input checks and error types as ``raycast_engine_cpu.py:40-43``.  Everything below the Python
+surface is the CUDA library behind ``include/lrc.h``.  There is no CPU path: without a B200 and a built
+``csrc/liblrc.so`` the constructor raises.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+
+from ..core import (Context, NoiseConfig, ScanResult, get_context, is_dual_axis, mesh_arrays)
+from ..lidar.sensors import DualAxisLidar, IndoorLidar
+from .base import RaycastEngineBase
+
+
+class RaycastEngineGPU(RaycastEngineBase):
+    """B200 ray-casting engine with the reference engine's interface.
+
+    Extras beyond the reference interface: ``simulate`` (a whole trajectory in one fused launch
+    sequence, device tensors out), ``last_scan`` (triangle ids / labels / ray indices of the most recent
+    frame) and ``cast_rays``.
+    """
+
+    def __init__(self, verbose=False, device: Optional[int] = None, cache_mesh: bool = True):
+        super().__init__()
+        self.verbose = verbose
+        self.cache_mesh = cache_mesh
+        self.ctx: Context = get_context(device)
+        self.last_scan: Optional[ScanResult] = None
+
+    # ---- reference interface ------------------------------------------------------------------
+    def rays_intersect_mesh(self, rays: np.ndarray, mesh):
+        """Closest hit of every ray; returns the hit points of the rays that hit, in ray order
+        (reference raycast_engine_cpu.py:24-73)."""
+        if not isinstance(rays, np.ndarray):
+            raise TypeError("rays must be a numpy array.")
+        if rays.ndim != 2 or rays.shape[1] != 6:
+            raise ValueError("rays must be a (N, 6) array.")
+        self._prepare(mesh)
+        res = self.ctx.rays_intersect(rays.astype(np.float32))
+        self.last_scan = res
+        return res.points.cpu().numpy()
+
+    def lidar_intersect_mesh(self, lidar, mesh):
+        """One LiDAR frame: rays -> closest hits -> range filter -> incident angles
+        (reference raycast_engine_cpu.py:75-111)."""
+        self._prepare(mesh)
+        if isinstance(lidar, IndoorLidar):
+            res = self.ctx.scan(lidar.pose[None], lidar.intrinsics, None)
+        elif isinstance(lidar, DualAxisLidar):
+            res = self.ctx.scan(lidar.pose[None], lidar.intrinsics, lidar.noise_config())
+        else:
+            # duck-typed sensor (the reference touches only get_rays(), pose[:3,3], intrinsics.max_range)
+            rays = lidar.get_rays()
+            if not isinstance(rays, np.ndarray):
+                raise TypeError("rays must be a numpy array.")
+            if rays.ndim != 2 or rays.shape[1] != 6:
+                raise ValueError("rays must be a (N, 6) array.")
+            res = self.ctx.scan_rays(rays.astype(np.float32), np.asarray(lidar.pose, dtype=np.float64)[:3, 3],
+                                     float(lidar.intrinsics.max_range))
+        self.last_scan = res
+        points = res.points.cpu().numpy()
+        incident = res.incident.cpu().numpy() if len(points) > 0 else np.empty(0)   # reference :109
+        return points, incident
+
+    # ---- extensions ---------------------------------------------------------------------------
+    def _prepare(self, mesh) -> None:
+        built = self.ctx.set_mesh(mesh, cache=self.cache_mesh)
+        if built and self.verbose:
+            print(f"[RaycastEngineGPU] LBVH built: {self.ctx.bvh_info()}")
+
+    def set_mesh(self, mesh) -> None:
+        self._prepare(mesh)
+
+    def cast_rays(self, rays: np.ndarray, mesh=None):
+        """Dense closest-hit query: (t_hit float32 [N] (+inf = miss), primitive_ids uint32 [N] (0xFFFFFFFF = miss))
+        -- the two ``RaycastingScene.cast_rays`` outputs the path uses (reference raycast_engine_cpu.py:51-53)."""
+        if mesh is not None:
+            self._prepare(mesh)
+        t, pid = self.ctx.cast_rays(np.ascontiguousarray(rays, dtype=np.float32))
+        return t.cpu().numpy(), pid.cpu().numpy().view(np.uint32)
+
+    def simulate(self, poses, intrinsics, mesh=None, noise: Optional[NoiseConfig] = None) -> ScanResult:
+        """All frames of a trajectory at once.  ``poses``: (P,4,4) float64 (``Waypoint.to_pose_matrix``).
+        Frame p of the result equals ``lidar_intersect_mesh(create_lidar(intrinsics, poses[p]), mesh)``."""
+        if mesh is not None:
+            self._prepare(mesh)
+        poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 4, 4)
+        res = self.ctx.scan(poses, intrinsics, noise)
+        self.last_scan = res
+        return res

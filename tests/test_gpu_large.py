@@ -1,0 +1,66 @@
+"""Parity at BASELINE.json's full sizes (1M-triangle office): oracle comparison on a pose subset, plus
+size-independent properties over the whole trajectory."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+MISS = 0xFFFFFFFF
+
+
+@pytest.fixture(scope="module")
+def office(lrc):
+    return lrc.synthetic.office()
+
+
+@pytest.fixture(scope="module")
+def office_poses(lrc):
+    return lrc.poses_from_waypoints(lrc.synthetic.office_waypoints(100))
+
+
+def test_c2_subset_bit_exact_vs_oracle(engine, lrc, orc, office, office_poses):
+    """BASELINE config 2 (32-line, 1M triangles): 3 of the 100 poses against the CPU oracle's SAH BVH."""
+    intr = lrc.Indoor8LineLidarIntrinsics.create_dense_32line()
+    sel = office_poses[[0, 37, 99]]
+    res = engine.simulate(sel, intr, office).numpy()
+    info = engine.ctx.bvh_info()
+    assert 990_000 <= info["num_tris"] <= 1_010_000 and info["max_depth"] < 64
+    scene = orc.OracleScene((office.vertices, office.triangles))
+    n_bad, n_all = 0, 0
+    for k in range(3):
+        rays = orc.gen_rays_single_axis(sel[k], intr.vertical_degrees, intr.horizontal_res)
+        t, pid = scene.cast_rays(rays)
+        fr = orc.epilogue_c(rays, t, pid, center=sel[k][:3, 3], max_range=intr.max_range, tri_label=office.triangle_labels)
+        a, b = res["frame_offset"][k], res["frame_offset"][k + 1]
+        assert b - a == len(fr.points)
+        assert np.array_equal(res["ray_idx"][a:b], fr.ray_idx)
+        same = res["prim_id"][a:b] == fr.prim_id
+        n_bad += int((~same).sum())
+        n_all += len(same)
+        assert np.array_equal(res["points"][a:b][same], fr.points[same])
+        assert np.abs(res["points"][a:b] - fr.points).max() <= 1e-4
+        np.testing.assert_allclose(res["incident"][a:b][same], fr.incident[same], rtol=0, atol=1e-9)
+        assert np.array_equal(res["label"][a:b], office.triangle_labels[res["prim_id"][a:b]])
+    assert n_bad / n_all <= 1e-5
+
+
+def test_c2_full_trajectory_properties(engine, lrc, office, office_poses):
+    """All 100 poses x 128000 rays: closed room => every ray hits; hits lie inside the room; frames are
+    ray-ordered; running the trajectory as two halves (the multi-GPU sharding) concatenates to the same bits."""
+    intr = lrc.Indoor8LineLidarIntrinsics.create_dense_32line()
+    res = engine.simulate(office_poses, intr, office)
+    out = res.numpy()
+    off = out["frame_offset"]
+    assert res.num_frames == 100 and off[0] == 0 and np.all(np.diff(off) > 0)
+    assert off[-1] >= 0.999 * 100 * 128000                      # closed shell, 25 m range: (almost) every ray returns
+    p = out["points"]
+    assert p[:, 0].min() > -1e-2 and p[:, 0].max() < 20.01 and p[:, 1].min() > -1e-2 and p[:, 1].max() < 15.01
+    assert p[:, 2].min() > -1e-2 and p[:, 2].max() < 3.01
+    for f in (0, 50, 99):
+        r = out["ray_idx"][off[f]:off[f + 1]].astype(np.int64)
+        assert np.all(np.diff(r) > 0) and r.max() < 128000
+    assert np.array_equal(out["label"], office.triangle_labels[out["prim_id"]])
+    a = engine.simulate(office_poses[:50], intr).numpy()
+    b = engine.simulate(office_poses[50:], intr).numpy()
+    for k in ("points", "incident", "prim_id", "label", "ray_idx"):
+        assert np.array_equal(np.concatenate([a[k], b[k]]), out[k]), k
+    assert np.array_equal(np.concatenate([a["frame_offset"], a["frame_offset"][-1] + b["frame_offset"][1:]]), off)
