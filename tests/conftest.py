@@ -26,6 +26,16 @@ def ulp_diff(a, b):
     return np.abs(ai - bi)
 
 
+def f32_mismatch(a, b, abs_floor=1e-9):
+    """Boolean mask of elements that differ by more than one float32 ulp (of the larger magnitude) AND by more
+    than ``abs_floor`` in absolute terms.  The floor matters for components of unit vectors that are ~1e-17 in
+    one libm and exactly 0 in another: many 'ulps' apart, physically identical."""
+    a = np.ascontiguousarray(a, dtype=np.float32).astype(np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float32).astype(np.float64)
+    tol = np.maximum(np.spacing(np.maximum(np.abs(a), np.abs(b)).astype(np.float32)).astype(np.float64), abs_floor)
+    return np.abs(a - b) > tol
+
+
 @pytest.fixture(scope="session")
 def golden():
     def load(name):

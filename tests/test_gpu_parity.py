@@ -6,7 +6,7 @@ and points."""
 import numpy as np
 import pytest
 
-from conftest import ulp_diff
+from conftest import f32_mismatch, ulp_diff
 
 pytestmark = pytest.mark.gpu
 MISS = 0xFFFFFFFF
@@ -36,8 +36,9 @@ def test_get_rays_single_axis_vs_reference_golden(engine, lrc, golden, golden_po
                                           horizontal_res=int(g[f"{preset}/W"]), vertical_res=len(g[f"{preset}/vertical_degrees"]))
     rays = lrc.IndoorLidar(intr, golden_poses[pose_name]).get_rays()
     assert rays.dtype == np.float32 and rays.shape == (int(g[f"{preset}/{pose_name}/n"]), 6)
-    d = ulp_diff(rays[::37], g[f"{preset}/{pose_name}/sample"])
-    assert d.max() <= 1 and (d > 0).mean() <= 1e-3      # device libm vs numpy: at most the last float32 bit
+    sample = g[f"{preset}/{pose_name}/sample"]
+    assert not f32_mismatch(rays[::37], sample).any()   # device libm vs numpy: at most the last float32 bit ...
+    assert (ulp_diff(rays[::37], sample) > 0).mean() <= 1e-3   # ... and almost always not even that
     np.testing.assert_allclose(rays.astype(np.float64).sum(0), g[f"{preset}/{pose_name}/sum"], atol=1e-3)
 
 
@@ -48,7 +49,7 @@ def test_get_rays_uniform_fov_vs_reference_golden(engine, lrc, golden, golden_po
         H, W = map(int, hw.split("x"))
         intr = lrc.Indoor8LineLidarIntrinsics(vertical_res=H, horizontal_res=W, vertical_degrees=None)
         rays = lrc.IndoorLidar(intr, golden_poses[pose_name]).get_rays()
-        assert ulp_diff(rays, g[key]).max() <= 1, key
+        assert not f32_mismatch(rays, g[key]).any(), key
 
 
 def test_get_rays_dual_axis_vs_reference_golden(engine, lrc, golden, golden_poses):
@@ -59,12 +60,13 @@ def test_get_rays_dual_axis_vs_reference_golden(engine, lrc, golden, golden_pose
     for pose_name, pose in golden_poses.items():
         rays = lrc.DualAxisLidar(intr, pose, seed=1).get_rays()
         assert rays.shape == (64000, 6)
-        d = ulp_diff(rays[::37], g[f"blk2go/{pose_name}/sample"])
-        assert d.max() <= 1 and (d > 0).mean() <= 1e-3
+        sample = g[f"blk2go/{pose_name}/sample"]
+        assert not f32_mismatch(rays[::37], sample).any()
+        assert (ulp_diff(rays[::37], sample) > 0).mean() <= 1e-3
     small = lrc.DualAxisLidarIntrinsics(point_rate=1000, scan_duration=0.5, num_vertical_lines=7, swing_frequency=3.0,
                                         swing_amplitude=0.3, angle_noise_std=0.0, dropout_probability=0.0)
     rays = lrc.DualAxisLidar(small, golden_poses["posed"], seed=1).get_rays()
-    assert ulp_diff(rays, g["small/rays"]).max() <= 1
+    assert not f32_mismatch(rays, g["small/rays"]).any()
 
 
 def test_dual_axis_noise_matches_oracle_philox(engine, lrc, orc, golden_poses):
@@ -76,8 +78,8 @@ def test_dual_axis_noise_matches_oracle_philox(engine, lrc, orc, golden_poses):
     ref, ref_keep = orc.gen_rays_dual_axis(golden_poses["posed"], orc.dual_params(intr), seed=0xC0FFEE, pose_idx=41, compact=False)
     assert np.array_equal(keep, ref_keep)
     assert abs(keep.mean() - 0.98) < 0.003
-    d = ulp_diff(rays, ref)
-    assert d.max() <= 2 and (d > 0).mean() <= 1e-3
+    assert not f32_mismatch(rays, ref).any()                      # Box-Muller through two different libms
+    assert (ulp_diff(rays, ref) > 0).mean() <= 1e-2
     lid = lrc.DualAxisLidar(intr, golden_poses["posed"], seed=0xC0FFEE, frame_index=41)
     assert np.array_equal(lid.get_rays(), rays[keep])
 
