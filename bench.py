@@ -261,6 +261,8 @@ def run_ours(args):
 
     engine = lrc.RaycastEngineGPU(device=local)
     ctx = engine.ctx
+    if args.variant is not None:
+        ctx.set_option("variant", args.variant)
     verts, tris, labels = lrc.mesh_arrays(mesh)
 
     # ---- one-off: BVH build time (CUDA events), resident inputs ----
@@ -452,6 +454,7 @@ def main():
     ap.add_argument("--tris", type=int, default=None, help="override the triangle count (debugging)")
     ap.add_argument("--poses", type=int, default=None, help="override poses per GPU (debugging)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--variant", type=int, default=None, help="traversal kernel variant (lrc_set_option)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--ref-frames", type=int, default=2, help="--impl reference: frames per step")
     args = ap.parse_args()

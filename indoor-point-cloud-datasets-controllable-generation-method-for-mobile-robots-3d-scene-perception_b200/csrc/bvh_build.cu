@@ -12,7 +12,8 @@
 //                    64 B node record (both child boxes + child links), tree height and SAH sum
 //
 // HBM layout produced:
-//   nodes: (T-1) x 4 float4   n0=(c0.lo.xyz, c0.hi.x) n1=(c0.hi.yz, c1.lo.xy) n2=(c1.lo.z, c1.hi.xyz)
+//   nodes: (T-1) x 4 float4   child boxes as centre c / half-extent h (h rounded up):
+//                             n0=(c0.xyz, h0.x) n1=(h0.yz, c1.xy) n2=(c1.z, h1.xyz)
 //                             n3=(link0, link1, 0, 0) as int bits; link >= 0 internal, < 0 leaf ~slot
 //   tris : T x 3 float4       (v0.xyz, orig id) (e1.xyz, 0) (e2.xyz, 0), slot = Morton rank
 #include "common.cuh"
@@ -290,6 +291,29 @@ __device__ __forceinline__ void load_box(int link, const float4* leaf_lo, const 
     else { lo = __ldcg(&node_lo[link]); hi = __ldcg(&node_hi[link]); }
 }
 
+// centre / half-extent form of a box; the half-extent is rounded UP so that [c-h, c+h] contains [lo, hi]
+__device__ __forceinline__ void to_centre_half(const float4 lo, const float4 hi, float c[3], float h[3])
+{
+    const float l[3] = {lo.x, lo.y, lo.z}, u[3] = {hi.x, hi.y, hi.z};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        c[k] = 0.5f * (l[k] + u[k]);
+        h[k] = fmaxf(__fsub_ru(u[k], c[k]), __fsub_ru(c[k], l[k]));
+    }
+}
+
+__device__ __forceinline__ void write_node(float4* __restrict__ rec, const float4 l0, const float4 h0, const float4 l1,
+                                           const float4 h1, int link0, int link1)
+{
+    float c0[3], e0[3], c1[3], e1[3];
+    to_centre_half(l0, h0, c0, e0);
+    to_centre_half(l1, h1, c1, e1);
+    rec[0] = make_float4(c0[0], c0[1], c0[2], e0[0]);
+    rec[1] = make_float4(e0[1], e0[2], c1[0], c1[1]);
+    rec[2] = make_float4(c1[2], e1[0], e1[1], e1[2]);
+    rec[3] = make_float4(__int_as_float(link0), __int_as_float(link1), 0.f, 0.f);
+}
+
 __global__ void k_refit(int n, const int* __restrict__ parent_leaf, const int* __restrict__ parent_node,
                         const int2* __restrict__ children, const float4* leaf_lo, const float4* leaf_hi, float4* node_lo,
                         float4* node_hi, int* flags, float4* __restrict__ nodes_out, BuildMeta* meta)
@@ -308,10 +332,7 @@ __global__ void k_refit(int n, const int* __restrict__ parent_leaf, const int* _
         float4 hi = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.f);
         node_lo[cur] = lo;
         node_hi[cur] = hi;
-        nodes_out[4 * (int64_t)cur + 0] = make_float4(l0.x, l0.y, l0.z, h0.x);
-        nodes_out[4 * (int64_t)cur + 1] = make_float4(h0.y, h0.z, l1.x, l1.y);
-        nodes_out[4 * (int64_t)cur + 2] = make_float4(l1.z, h1.x, h1.y, h1.z);
-        nodes_out[4 * (int64_t)cur + 3] = make_float4(__int_as_float(ch.x), __int_as_float(ch.y), 0.f, 0.f);
+        write_node(nodes_out + 4 * (int64_t)cur, l0, h0, l1, h1, ch.x, ch.y);
         float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z;
         atomicAdd(&meta->area_sum, (double)(2.f * (ex * ey + ey * ez + ez * ex)));
         int up = parent_node[cur];
@@ -329,10 +350,7 @@ __global__ void k_refit(int n, const int* __restrict__ parent_leaf, const int* _
 __global__ void k_single_leaf_root(const float4* leaf_lo, const float4* leaf_hi, float4* nodes_out, BuildMeta* meta)
 {
     float4 l = leaf_lo[0], h = leaf_hi[0];
-    nodes_out[0] = make_float4(l.x, l.y, l.z, h.x);
-    nodes_out[1] = make_float4(h.y, h.z, l.x, l.y);
-    nodes_out[2] = make_float4(l.z, h.x, h.y, h.z);
-    nodes_out[3] = make_float4(__int_as_float(~0), __int_as_float(~0), 0.f, 0.f);
+    write_node(nodes_out, l, h, l, h, ~0, ~0);
     meta->height = 1;
     float ex = h.x - l.x, ey = h.y - l.y, ez = h.z - l.z;
     meta->area_sum = 2.0 * (ex * ey + ey * ez + ez * ex);

@@ -164,7 +164,7 @@ __global__ void k_gen_rays(RayGen g, int64_t n, float* __restrict__ rays, uint8_
 // OUT_DENSE: write (t_hit, prim_id) per ray (cast_rays).  Otherwise write the float32 hit point and the
 // triangle id as one float4 per ray for the epilogue:
 //     d^ = d / sqrt((dx*dx + dy*dy) + dz*dz) ; p = o + d^ * t      (raycast_engine_cpu.py:57,62; separate roundings)
-template <int MODE, bool COUNT, bool OUT_DENSE>
+template <int MODE, bool COUNT, bool OUT_DENSE, int VARIANT>
 __global__ void __launch_bounds__(128)
 k_trace(RayGen g, const float4* __restrict__ nodes, const float4* __restrict__ tris, int64_t n, int has_tris,
         float4* __restrict__ hp, float* __restrict__ t_hit, uint32_t* __restrict__ prim_id, unsigned long long* counters)
@@ -177,7 +177,7 @@ k_trace(RayGen g, const float4* __restrict__ nodes, const float4* __restrict__ t
         float t = LRC_INF;
         uint32_t id = LRC_MISS_ID;
         if (ray.keep && has_tris) {
-            trace_ray<COUNT>(nodes, tris, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, t, id, nn, nt);
+            trace_ray<VARIANT, COUNT>(nodes, tris, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, t, id, nn, nt);
             nr = 1;
             nh = id != LRC_MISS_ID;
         }
@@ -400,11 +400,14 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, int64_t n, float4* hp, float* t_
     const int TB = 128;
     const unsigned grid = (unsigned)((n + TB - 1) / TB);
     const int has_tris = ctx->T > 0;
+#define LRC_LAUNCH_TRACE(COUNT, VARIANT) \
+    k_trace<MODE, COUNT, DENSE, VARIANT><<<grid, TB, 0, stream>>>(g, ctx->nodes, ctx->tris, n, has_tris, hp, t_hit, prim, ctx->d_counters)
     if (ctx->counting) {
-        k_trace<MODE, true, DENSE><<<grid, TB, 0, stream>>>(g, ctx->nodes, ctx->tris, n, has_tris, hp, t_hit, prim, ctx->d_counters);
+        if (ctx->opt_variant == 0) LRC_LAUNCH_TRACE(true, 0); else LRC_LAUNCH_TRACE(true, 1);
     } else {
-        k_trace<MODE, false, DENSE><<<grid, TB, 0, stream>>>(g, ctx->nodes, ctx->tris, n, has_tris, hp, t_hit, prim, ctx->d_counters);
+        if (ctx->opt_variant == 0) LRC_LAUNCH_TRACE(false, 0); else LRC_LAUNCH_TRACE(false, 1);
     }
+#undef LRC_LAUNCH_TRACE
     LRC_CHECK_LAUNCH(ctx, "k_trace");
     return LRC_OK;
 }
@@ -591,7 +594,11 @@ extern "C" int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value)
 {
     if (!ctx || !key) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_option: NULL argument");
     if (!strcmp(key, "chunk_rays")) { if (value < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "chunk_rays must be >= 1"); ctx->opt_chunk_rays = value; return LRC_OK; }
-    if (!strcmp(key, "variant")) { ctx->opt_variant = value; return LRC_OK; }
+    if (!strcmp(key, "variant")) {
+        if (value < 0 || value > 1) return lrc_fail(ctx, LRC_ERR_INVALID, "variant must be 0 or 1");
+        ctx->opt_variant = value;
+        return LRC_OK;
+    }
     return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_option: unknown key '%s'", key);
 }
 

@@ -8,6 +8,13 @@
 //     hit <=> det > 0 && U >= 0 && V >= 0 && (U + V) <= det && W >= 0 ;  t = W / det  (IEEE division)
 // Closest hit: smallest t, ties -> smallest original triangle id.  Two-sided, t >= 0, t in units of |d|
 // (Embree contract behind reference raycast_engine_cpu.py:51; the reference passes directions as given).
+//
+// Node record (64 B, see bvh_build.cu): child boxes are stored as CENTRE / HALF-EXTENT, half-extents
+// rounded up.  The slab test then is, per axis,
+//     tc = fma(c, inv, -o*inv) ; tnear = fma(-h, |inv|, tc) ; tfar = fma(h, |inv|, tc)
+// i.e. 9 FFMA + 4 FMNMX(3) per box instead of 6 FFMA + 10 FMNMX for the min/max form: the min/max
+// selection by ray direction is folded into |inv|.  On sm_100 FMNMX issues on the ALU pipe, which ncu
+// showed to be the busiest pipe of the min/max form (profiles/r01_*), while the FMA pipe had headroom.
 #pragma once
 #include "common.cuh"
 
@@ -45,60 +52,106 @@ __device__ __forceinline__ float safe_inv(float d)
     return __frcp_rn(d);
 }
 
-// Slab test of one child box against the ray in (inv, ood = o * inv) form; conservative because every
-// leaf box carries an absolute pad that dwarfs the rounding of these six FMAs (see bvh_build.cu).
-__device__ __forceinline__ bool slab(float lox, float loy, float loz, float hix, float hiy, float hiz, float ix, float iy,
-                                     float iz, float oox, float ooy, float ooz, float tmax, float& tnear)
+// per-ray constants of the slab test
+struct RaySlab {
+    float ix, iy, iz;      // 1/d (clamped away from 0)
+    float ax, ay, az;      // |1/d|
+    float nx, ny, nz;      // -o/d
+};
+
+__device__ __forceinline__ RaySlab make_slab(float ox, float oy, float oz, float dx, float dy, float dz)
 {
-    float ax = fmaf(lox, ix, -oox), bx = fmaf(hix, ix, -oox);
-    float ay = fmaf(loy, iy, -ooy), by = fmaf(hiy, iy, -ooy);
-    float az = fmaf(loz, iz, -ooz), bz = fmaf(hiz, iz, -ooz);
-    float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
-    float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+    RaySlab s;
+    s.ix = safe_inv(dx); s.iy = safe_inv(dy); s.iz = safe_inv(dz);
+    s.ax = fabsf(s.ix); s.ay = fabsf(s.iy); s.az = fabsf(s.iz);
+    s.nx = -(ox * s.ix); s.ny = -(oy * s.iy); s.nz = -(oz * s.iz);
+    // keep the three products in registers: without this ptxas re-multiplies them at every node
+    asm volatile("" : "+f"(s.nx), "+f"(s.ny), "+f"(s.nz));
+    return s;
+}
+
+// centre/half-extent slab test; conservative because every leaf box carries an absolute pad that dwarfs the
+// rounding of these nine FMAs and half-extents are rounded up (see bvh_build.cu).
+__device__ __forceinline__ bool slab_ch(float cx, float cy, float cz, float hx, float hy, float hz, const RaySlab& s,
+                                        float tmax, float& tnear)
+{
+    const float tcx = fmaf(cx, s.ix, s.nx), tcy = fmaf(cy, s.iy, s.ny), tcz = fmaf(cz, s.iz, s.nz);
+    const float n0 = fmaf(-hx, s.ax, tcx), n1 = fmaf(-hy, s.ay, tcy), n2 = fmaf(-hz, s.az, tcz);
+    const float f0 = fmaf(hx, s.ax, tcx), f1 = fmaf(hy, s.ay, tcy), f2 = fmaf(hz, s.az, tcz);
+    const float t0 = fmaxf(fmaxf(n0, n1), fmaxf(n2, 0.f));
+    const float t1 = fminf(fminf(f0, f1), fminf(f2, tmax));
     tnear = t0;
     return t0 <= t1;
 }
 
-// Stack-based closest-hit traversal.  nodes/tris layout: see bvh_build.cu.
+#define LRC_SENTINEL ((int)0x80000000)   // a "leaf" link no tree contains: ~0x80000000 = 0x7fffffff slots
+
+__device__ __forceinline__ void leaf_test(const float4* __restrict__ tris, int link, float ox, float oy, float oz, float dx,
+                                          float dy, float dz, float& best_t, uint32_t& best_id)
+{
+    const float4* tp = tris + 3 * (int64_t)(~link);
+    const float4 v0 = __ldg(tp + 0), e1 = __ldg(tp + 1), e2 = __ldg(tp + 2);
+    float t;
+    if (mt_hit(ox, oy, oz, dx, dy, dz, v0, e1, e2, t)) {
+        const uint32_t id = __float_as_uint(v0.w);
+        if (t < best_t || (t == best_t && id < best_id)) { best_t = t; best_id = id; }
+    }
+}
+
+// One step at an inner node: returns the next link (child to descend into, or a popped entry, or the sentinel).
 template <bool COUNT>
+__device__ __forceinline__ int inner_step(const float4* __restrict__ nodes, int cur, const RaySlab& s, float best_t,
+                                          int* stack, int& sp, unsigned& n_nodes)
+{
+    const float4* np = nodes + 4 * (int64_t)cur;
+    const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
+    const float2 n3 = __ldg(reinterpret_cast<const float2*>(np + 3));
+    if (COUNT) ++n_nodes;
+    float t0, t1;
+    const bool h0 = slab_ch(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, s, best_t, t0);
+    const bool h1 = slab_ch(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, s, best_t, t1);
+    const int l0 = __float_as_int(n3.x), l1 = __float_as_int(n3.y);
+    if (h0 && h1) {
+        const bool swp = t1 < t0;              // nearer child first, farther one on the stack
+        stack[sp++] = swp ? l0 : l1;
+        return swp ? l1 : l0;
+    }
+    if (h0) return l0;
+    if (h1) return l1;
+    return sp > 0 ? stack[--sp] : LRC_SENTINEL;
+}
+
+// Stack-based closest-hit traversal.  VARIANT 0: one node (inner or leaf) per loop trip ("if-if").
+// VARIANT 1: "while-while" -- run down inner nodes until a leaf (or the end) is reached, then test the leaf.
+template <int VARIANT, bool COUNT>
 __device__ __forceinline__ void trace_ray(const float4* __restrict__ nodes, const float4* __restrict__ tris, float ox,
                                           float oy, float oz, float dx, float dy, float dz, float& best_t,
                                           uint32_t& best_id, unsigned& n_nodes, unsigned& n_tris)
 {
     best_t = LRC_INF;
     best_id = LRC_MISS_ID;
-    const float ix = safe_inv(dx), iy = safe_inv(dy), iz = safe_inv(dz);
-    const float oox = ox * ix, ooy = oy * iy, ooz = oz * iz;
+    const RaySlab s = make_slab(ox, oy, oz, dx, dy, dz);
     int stack[LRC_STACK_DEPTH];
     int sp = 0;
     int cur = 0;
-    for (;;) {
-        if (cur >= 0) {
-            const float4* np = nodes + 4 * (int64_t)cur;
-            const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
-            if (COUNT) ++n_nodes;
-            float t0, t1;
-            const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ix, iy, iz, oox, ooy, ooz, best_t, t0);
-            const bool h1 = slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, ix, iy, iz, oox, ooy, ooz, best_t, t1);
-            const int l0 = __float_as_int(n3.x), l1 = __float_as_int(n3.y);
-            if (h0 && h1) {
-                const bool swp = t1 < t0;          // nearer child first, farther one on the stack
-                cur = swp ? l1 : l0;
-                stack[sp++] = swp ? l0 : l1;
-                continue;
-            }
-            if (h0 || h1) { cur = h0 ? l0 : l1; continue; }
-        } else {
-            const float4* tp = tris + 3 * (int64_t)(~cur);
-            const float4 v0 = __ldg(tp + 0), e1 = __ldg(tp + 1), e2 = __ldg(tp + 2);
-            if (COUNT) ++n_tris;
-            float t;
-            if (mt_hit(ox, oy, oz, dx, dy, dz, v0, e1, e2, t)) {
-                const uint32_t id = __float_as_uint(v0.w);
-                if (t < best_t || (t == best_t && id < best_id)) { best_t = t; best_id = id; }
+    if (VARIANT == 0) {
+        while (cur != LRC_SENTINEL) {
+            if (cur >= 0) {
+                cur = inner_step<COUNT>(nodes, cur, s, best_t, stack, sp, n_nodes);
+            } else {
+                if (COUNT) ++n_tris;
+                leaf_test(tris, cur, ox, oy, oz, dx, dy, dz, best_t, best_id);
+                cur = sp > 0 ? stack[--sp] : LRC_SENTINEL;
             }
         }
-        if (sp == 0) break;
-        cur = stack[--sp];
+    } else {
+        while (cur != LRC_SENTINEL) {
+            while (cur >= 0) cur = inner_step<COUNT>(nodes, cur, s, best_t, stack, sp, n_nodes);
+            if (cur != LRC_SENTINEL) {
+                if (COUNT) ++n_tris;
+                leaf_test(tris, cur, ox, oy, oz, dx, dy, dz, best_t, best_id);
+                cur = sp > 0 ? stack[--sp] : LRC_SENTINEL;
+            }
+        }
     }
 }
