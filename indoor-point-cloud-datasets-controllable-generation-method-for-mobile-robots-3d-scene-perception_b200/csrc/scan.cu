@@ -1,5 +1,5 @@
-// scan.cu -- ray generation, traversal launches and the fused epilogue (label gather + range filter +
-// incident angle + ordered compaction).  Together these replace, per waypoint,
+// scan.cu -- ray generation, traversal launches (with the frame arithmetic: point reconstruction, range filter,
+// incident angle) and the ordered compaction with label gather.  Together these replace, per waypoint,
 //     RaycastEngineCPU.lidar_intersect_mesh / rays_intersect_mesh  (reference raycast_engine_cpu.py:24-111)
 // and IndoorLidar.get_rays / DualAxisLidar.get_rays                 (reference indoor_lidar.py:27-131,224-319).
 #include "traverse.cuh"
@@ -9,10 +9,6 @@ char g_lrc_global_err[512] = {0};
 namespace {
 
 constexpr double PI_D = 3.141592653589793;
-constexpr int EPI_THREADS = 256;
-constexpr int EPI_ITEMS = 4;
-constexpr int EPI_TILE = EPI_THREADS * EPI_ITEMS;
-constexpr unsigned long long ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_MASK = (1ull << 62) - 1;
 
 enum { MODE_SINGLE = 0, MODE_DUAL = 1, MODE_RAYS = 2 };
 
@@ -161,16 +157,29 @@ __global__ void k_gen_rays(RayGen g, int64_t n, float* __restrict__ rays, uint8_
 }
 
 // ---- traversal kernels -------------------------------------------------------------------------------
-// OUT_DENSE: write (t_hit, prim_id) per ray (cast_rays).  Otherwise write the float32 hit point and the
-// triangle id as one float4 per ray for the epilogue:
-//     d^ = d / sqrt((dx*dx + dy*dy) + dz*dz) ; p = o + d^ * t      (raycast_engine_cpu.py:57,62; separate roundings)
+// Frame-level arithmetic that rides in the traversal kernel (the float64 pipe is otherwise idle there):
+//     d^ = d / sqrt((dx*dx + dy*dy) + dz*dz) ; p = o + d^ * t          float32, separate roundings (raycast_engine_cpu.py:57,62)
+//     dist = sqrt(((p - c)^2).sum()) in float64 from the float32 point ; keep <=> dist < max_range   (strict, :95-97)
+//     incident = degrees(arccos(|(p - c)_z / dist|))                   float64 (:100-107)
+struct FrameMath {
+    double max_range;          // < 0: no range filter, no incident angle (rays_intersect_mesh)
+    double cx, cy, cz;         // frame centre for MODE_RAYS; scan modes read pose[:3,3]
+};
+
+constexpr int TRACE_THREADS = 128;
+
+// OUT_DENSE: write (t_hit, prim_id) per ray (cast_rays).  Otherwise, per ray, the float32 hit point + triangle id
+// (float4; id = MISS when the ray missed, was dropped or failed the range test), the incident angle, and per BLOCK
+// the number of kept rays (block_count) -- the first stage of the ordered compaction.
 template <int MODE, bool COUNT, bool OUT_DENSE, int VARIANT>
-__global__ void __launch_bounds__(128)
-k_trace(RayGen g, const float4* __restrict__ nodes, const float4* __restrict__ tris, int64_t n, int has_tris,
-        float4* __restrict__ hp, float* __restrict__ t_hit, uint32_t* __restrict__ prim_id, unsigned long long* counters)
+__global__ void __launch_bounds__(TRACE_THREADS)
+k_trace(RayGen g, FrameMath fm, const float4* __restrict__ nodes, const float4* __restrict__ tris, int64_t n, int has_tris,
+        float4* __restrict__ hp, double* __restrict__ inc_out, unsigned* __restrict__ block_count, float* __restrict__ t_hit,
+        uint32_t* __restrict__ prim_id, unsigned long long* counters)
 {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned nn = 0, nt = 0, nr = 0, nh = 0;
+    bool keep = false;
     if (idx < n) {
         int64_t pose; int r;
         Ray ray = gen_ray<MODE>(g, idx, pose, r);
@@ -186,16 +195,34 @@ k_trace(RayGen g, const float4* __restrict__ nodes, const float4* __restrict__ t
             prim_id[idx] = id;
         } else {
             float4 o = make_float4(0.f, 0.f, 0.f, __uint_as_float(LRC_MISS_ID));
+            double inc = 0.0;
             if (id != LRC_MISS_ID) {
                 if (g.range_std > 0.0) t = __fadd_rn(t, (float)(g.range_std * range_normal(g, pose, r)));
                 float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ray.dx, ray.dx), __fmul_rn(ray.dy, ray.dy)), __fmul_rn(ray.dz, ray.dz)));
                 o.x = __fadd_rn(ray.ox, __fmul_rn(__fdiv_rn(ray.dx, nrm), t));
                 o.y = __fadd_rn(ray.oy, __fmul_rn(__fdiv_rn(ray.dy, nrm), t));
                 o.z = __fadd_rn(ray.oz, __fmul_rn(__fdiv_rn(ray.dz, nrm), t));
-                o.w = __uint_as_float(id);
+                keep = true;
+                if (fm.max_range >= 0.0) {
+                    double cx = fm.cx, cy = fm.cy, cz = fm.cz;
+                    if (MODE != MODE_RAYS) {
+                        const double* M = g.poses + 16 * (g.pose0 + pose);
+                        cx = M[3]; cy = M[7]; cz = M[11];
+                    }
+                    const double ddx = __dsub_rn((double)o.x, cx), ddy = __dsub_rn((double)o.y, cy), ddz = __dsub_rn((double)o.z, cz);
+                    const double dist = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz)));
+                    keep = dist < fm.max_range;
+                    if (inc_out) inc = __dmul_rn(acos(fabs(__ddiv_rn(ddz, dist))), 180.0 / PI_D);
+                }
+                if (keep) o.w = __uint_as_float(id);
             }
             hp[idx] = o;
+            if (inc_out) inc_out[idx] = inc;
         }
+    }
+    if (!OUT_DENSE) {
+        const int c = __syncthreads_count(keep ? 1 : 0);
+        if (threadIdx.x == 0) block_count[blockIdx.x] = (unsigned)c;
     }
     if (COUNT) {
 #pragma unroll
@@ -236,150 +263,102 @@ __global__ void k_brute(const float* __restrict__ rays, int64_t n, const float4*
     prim_id[idx] = best_id;
 }
 
-// ---- fused epilogue ----------------------------------------------------------------------------------
-// Per ray: range filter on the float64 distance recomputed from the float32 point with strict '<'
-// (raycast_engine_cpu.py:95-97), incident = degrees(arccos(|dz/dist|)) (:100-107), label gather by triangle
-// id, and ORDER-PRESERVING compaction (the reference's boolean-mask indexing keeps ray order, :71,:97):
-// thread-local counts -> warp shuffle scan -> block scan -> single-pass chained scan across tiles with
-// decoupled look-back (tiles take tickets so that every predecessor is already resident).
-struct EpiParams {
+// ---- ordered compaction: stage 2 (scan of block counts) and stage 3 (streaming scatter) ------------------
+// The reference's boolean-mask indexing keeps ray order (raycast_engine_cpu.py:71,:97), so the compaction must be
+// order-preserving: per-block keep counts (written by k_trace) -> exclusive scan -> each block scatters its kept
+// rays at base + warp-ballot prefix.  No atomics decide positions, so the output order is deterministic.
+__global__ void __launch_bounds__(1024) k_scan_counts(const unsigned* __restrict__ counts, unsigned* __restrict__ base,
+                                                      int64_t nb, const long long* __restrict__ run_in,
+                                                      long long* __restrict__ run_out, int64_t* __restrict__ frame_offset_last)
+{
+    __shared__ unsigned warp_sums[32];
+    __shared__ unsigned carry;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0u;
+    __syncthreads();
+    for (int64_t b0 = 0; b0 < nb; b0 += 1024) {
+        const int64_t i = b0 + threadIdx.x;
+        const unsigned v = i < nb ? counts[i] : 0u;
+        unsigned incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            unsigned sv = warp_sums[lane], si = sv;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned t = __shfl_up_sync(0xffffffffu, si, o);
+                if (lane >= o) si += t;
+            }
+            warp_sums[lane] = si - sv;
+        }
+        __syncthreads();
+        const unsigned excl = incl - v + warp_sums[w] + carry;
+        if (i < nb) base[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const long long total = *run_in + (long long)carry;
+        *run_out = total;
+        if (frame_offset_last) *frame_offset_last = total;
+    }
+}
+
+struct CompactParams {
     const float4* hp;
+    const double* inc;
+    const unsigned* base;      // exclusive scan of the per-block keep counts of this launch
+    const long long* run_in;   // points emitted by earlier launches of this call
     int64_t n;                 // rays in this launch
     int64_t ray0;              // global index of the first ray of this launch
     int64_t N;                 // rays per frame
-    int64_t P;                 // total frames of the whole call
-    const double* poses;       // frame centres come from here ...
-    double cx, cy, cz;         // ... or from here when poses == NULL
-    double max_range;          // < 0: no range filter, no incident angle (rays_intersect_mesh)
     const uint32_t* labels;
     lrc_out out;
-    unsigned long long* status;
-    unsigned* ticket;
-    const long long* run_in;   // points already emitted by earlier launches of this call
-    long long* run_out;
-    int last;                  // this launch finishes the call: write frame_offset[P]
 };
 
-__global__ void __launch_bounds__(EPI_THREADS) k_epilogue(EpiParams q)
+__global__ void __launch_bounds__(TRACE_THREADS) k_compact(CompactParams q)
 {
-    __shared__ unsigned s_tile;
-    __shared__ int s_warp[EPI_THREADS / 32];
-    __shared__ long long s_prefix;
-    if (threadIdx.x == 0) s_tile = atomicAdd(q.ticket, 1u);
-    __syncthreads();
-    const int64_t tile = s_tile;
-    const int64_t first = tile * EPI_TILE + (int64_t)threadIdx.x * EPI_ITEMS;
-
-    float4 h[EPI_ITEMS];
-    double inc[EPI_ITEMS];
-    bool keep[EPI_ITEMS];
-    int cnt = 0;
-#pragma unroll
-    for (int k = 0; k < EPI_ITEMS; ++k) {
-        const int64_t i = first + k;
-        keep[k] = false;
-        inc[k] = 0.0;
-        if (i < q.n) {
-            h[k] = __ldcs(q.hp + i);
-            if (__float_as_uint(h[k].w) != LRC_MISS_ID) {
-                keep[k] = true;
-                if (q.max_range >= 0.0) {
-                    double cx = q.cx, cy = q.cy, cz = q.cz;
-                    if (q.poses) {
-                        const double* M = q.poses + 16 * ((q.ray0 + i) / q.N);
-                        cx = M[3]; cy = M[7]; cz = M[11];
-                    }
-                    const double ddx = __dsub_rn((double)h[k].x, cx), ddy = __dsub_rn((double)h[k].y, cy),
-                                 ddz = __dsub_rn((double)h[k].z, cz);
-                    const double dist = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz)));
-                    keep[k] = dist < q.max_range;
-                    inc[k] = __dmul_rn(acos(fabs(__ddiv_rn(ddz, dist))), 180.0 / PI_D);
-                }
-            }
-        }
-        cnt += keep[k] ? 1 : 0;
-    }
-    // block-level exclusive scan of per-thread counts
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_warp[w] = incl;
-    __syncthreads();
-    int warp_off = 0, total = 0;
-#pragma unroll
-    for (int k = 0; k < EPI_THREADS / 32; ++k) {
-        int v = s_warp[k];
-        if (k < w) warp_off += v;
-        total += v;
-    }
-    const int local_excl = warp_off + incl - cnt;
-
-    // chained scan across tiles (decoupled look-back), warp 0 only
-    if (w == 0) {
-        long long excl = 0;
-        if (tile > 0) {
-            if (lane == 0) {
-                *((volatile unsigned long long*)&q.status[tile]) = ST_AGG | (unsigned long long)total;
-            }
-            int64_t look = tile - 1;
-            for (;;) {
-                const int64_t j = look - lane;
-                unsigned long long s = ST_INC;   // virtual "inclusive 0" in front of tile 0
-                if (j >= 0) {
-                    do { s = *((volatile unsigned long long*)&q.status[j]); } while ((s >> 62) == 0ull);
-                }
-                const unsigned inc_mask = __ballot_sync(0xffffffffu, (s >> 62) == 2ull);
-                long long v = (long long)(s & ST_MASK);
-                if (inc_mask) {
-                    const int stop = __ffs(inc_mask) - 1;   // nearest predecessor holding an inclusive prefix
-                    if (lane > stop) v = 0;
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                excl += v;
-                if (inc_mask) break;
-                look -= 32;
-            }
-        }
-        if (lane == 0) {
-            *((volatile unsigned long long*)&q.status[tile]) = ST_INC | (unsigned long long)(excl + total);
-            s_prefix = excl;
-        }
-    }
-    __syncthreads();
+    __shared__ int s_warp[TRACE_THREADS / 32];
     const long long run0 = *q.run_in;
-    long long pos = run0 + s_prefix + local_excl;
-#pragma unroll
-    for (int k = 0; k < EPI_ITEMS; ++k) {
-        const int64_t i = first + k;
-        if (i < q.n) {
-            const int64_t gidx = q.ray0 + i;
-            const int64_t frame = gidx / q.N;
-            const int64_t r = gidx - frame * q.N;
-            if (r == 0) q.out.frame_offset[frame] = pos;
-            if (keep[k]) {
-                if (pos < q.out.capacity) {
-                    const uint32_t id = __float_as_uint(h[k].w);
-                    q.out.xyz[3 * pos + 0] = h[k].x;
-                    q.out.xyz[3 * pos + 1] = h[k].y;
-                    q.out.xyz[3 * pos + 2] = h[k].z;
-                    if (q.out.incident_deg) q.out.incident_deg[pos] = inc[k];
-                    if (q.out.prim_id) q.out.prim_id[pos] = id;
-                    if (q.out.label) q.out.label[pos] = __ldg(q.labels + id);
-                    if (q.out.ray_idx) q.out.ray_idx[pos] = (uint32_t)r;
-                }
-                ++pos;
-            }
-        }
+    const unsigned blk_base = q.base[blockIdx.x];
+    const int64_t i = (int64_t)blockIdx.x * TRACE_THREADS + threadIdx.x;
+    float4 h = make_float4(0.f, 0.f, 0.f, __uint_as_float(LRC_MISS_ID));
+    double inc = 0.0;
+    if (i < q.n) {
+        h = __ldcs(q.hp + i);
+        if (q.inc) inc = __ldcs(q.inc + i);
     }
-    // the tile that owns the last ray of this launch closes the books
-    if (first <= q.n - 1 && q.n - 1 < first + EPI_ITEMS) {
-        *q.run_out = pos;
-        if (q.last) q.out.frame_offset[q.P] = pos;
+    const uint32_t id = __float_as_uint(h.w);
+    const bool keep = id != LRC_MISS_ID;
+    const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) s_warp[w] = __popc(ballot);
+    __syncthreads();
+    int warp_off = 0;
+#pragma unroll
+    for (int k = 0; k < TRACE_THREADS / 32; ++k)
+        if (k < w) warp_off += s_warp[k];
+    const long long pos = run0 + blk_base + warp_off + __popc(ballot & ((1u << lane) - 1u));
+    if (i < q.n) {
+        const int64_t gidx = q.ray0 + i;
+        const int64_t frame = gidx / q.N;
+        const int64_t r = gidx - frame * q.N;
+        if (r == 0) q.out.frame_offset[frame] = pos;
+        if (keep && pos < q.out.capacity) {
+            q.out.xyz[3 * pos + 0] = h.x;
+            q.out.xyz[3 * pos + 1] = h.y;
+            q.out.xyz[3 * pos + 2] = h.z;
+            if (q.out.incident_deg) q.out.incident_deg[pos] = inc;
+            if (q.out.prim_id) q.out.prim_id[pos] = id;
+            if (q.out.label) q.out.label[pos] = __ldg(q.labels + id);
+            if (q.out.ray_idx) q.out.ray_idx[pos] = (uint32_t)r;
+        }
     }
 }
 
@@ -394,14 +373,15 @@ int ensure_counters(lrc_ctx* ctx)
 }
 
 template <int MODE, bool DENSE>
-int launch_trace(lrc_ctx* ctx, const RayGen& g, int64_t n, float4* hp, float* t_hit, uint32_t* prim, cudaStream_t stream)
+int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, float4* hp, double* inc, unsigned* block_count,
+                 float* t_hit, uint32_t* prim, cudaStream_t stream)
 {
     if (n <= 0) return LRC_OK;
-    const int TB = 128;
+    const int TB = TRACE_THREADS;
     const unsigned grid = (unsigned)((n + TB - 1) / TB);
     const int has_tris = ctx->T > 0;
 #define LRC_LAUNCH_TRACE(COUNT, VARIANT) \
-    k_trace<MODE, COUNT, DENSE, VARIANT><<<grid, TB, 0, stream>>>(g, ctx->nodes, ctx->tris, n, has_tris, hp, t_hit, prim, ctx->d_counters)
+    k_trace<MODE, COUNT, DENSE, VARIANT><<<grid, TB, 0, stream>>>(g, fm, ctx->nodes, ctx->tris, n, has_tris, hp, inc, block_count, t_hit, prim, ctx->d_counters)
     if (ctx->counting) {
         if (ctx->opt_variant == 0) LRC_LAUNCH_TRACE(true, 0); else LRC_LAUNCH_TRACE(true, 1);
     } else {
@@ -419,10 +399,11 @@ int check_out(lrc_ctx* ctx, const lrc_out* out, int64_t need)
     return LRC_OK;
 }
 
-// Shared driver of all scan-type entry points: chunked trace -> epilogue with a running output offset.
+// Shared driver of all scan-type entry points: per chunk of whole frames, trace (+ block counts) -> scan of the
+// counts -> streaming compaction, with a running output offset carried in device memory (no host round trip).
 template <int MODE>
-int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* poses_for_center, const double* h_center,
-             double max_range, lrc_out* out, cudaStream_t stream)
+int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_center, double max_range, lrc_out* out,
+             cudaStream_t stream)
 {
     const int64_t total = P * N;
     int rc = check_out(ctx, out, total);
@@ -432,46 +413,52 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* poses_f
         LRC_CUDA(ctx, cudaMemsetAsync(out->frame_offset, 0, sizeof(int64_t) * (P + 1), stream));
         return LRC_OK;
     }
-    // chunk by whole frames where possible so scratch stays bounded (16 B per ray)
+    // chunk by whole frames so that scratch stays bounded (24 B per ray)
     int64_t frames_per_chunk = ctx->opt_chunk_rays / N;
     if (frames_per_chunk < 1) frames_per_chunk = 1;
     if (MODE == MODE_RAYS) frames_per_chunk = P;   // a single explicit frame
     const int64_t n_chunks = (P + frames_per_chunk - 1) / frames_per_chunk;
     const int64_t chunk_rays = frames_per_chunk * N;
-    const int64_t max_tiles = (chunk_rays + EPI_TILE - 1) / EPI_TILE;
-    if ((rc = lrc_grow(ctx, &ctx->scratch, &ctx->scratch_bytes, sizeof(float4) * (size_t)chunk_rays))) return rc;
-    const size_t st_bytes = align_up(sizeof(unsigned long long) * (size_t)max_tiles, 256);
-    const size_t need2 = st_bytes * 2 + 256 + sizeof(long long) * (size_t)(n_chunks + 1);
+    const int64_t max_blocks = (chunk_rays + TRACE_THREADS - 1) / TRACE_THREADS;
+    const bool want_inc = out->incident_deg != nullptr && max_range >= 0.0;
+    const size_t hp_bytes = align_up(sizeof(float4) * (size_t)chunk_rays, 256);
+    const size_t inc_bytes = want_inc ? align_up(sizeof(double) * (size_t)chunk_rays, 256) : 0;
+    if ((rc = lrc_grow(ctx, &ctx->scratch, &ctx->scratch_bytes, hp_bytes + inc_bytes))) return rc;
+    const size_t cnt_bytes = align_up(sizeof(unsigned) * (size_t)max_blocks, 256);
+    const size_t need2 = 2 * cnt_bytes + sizeof(long long) * (size_t)(n_chunks + 1);
     if ((rc = lrc_grow(ctx, &ctx->scratch2, &ctx->scratch2_bytes, need2))) return rc;
     char* b2 = (char*)ctx->scratch2;
-    long long* run = (long long*)(b2 + 2 * st_bytes + 256);
+    unsigned* counts = (unsigned*)b2;
+    unsigned* base = (unsigned*)(b2 + cnt_bytes);
+    long long* run = (long long*)(b2 + 2 * cnt_bytes);
     LRC_CUDA(ctx, cudaMemsetAsync(run, 0, sizeof(long long), stream));
     float4* hp = (float4*)ctx->scratch;
+    double* inc = want_inc ? (double*)((char*)ctx->scratch + hp_bytes) : nullptr;
+    FrameMath fm;
+    fm.max_range = max_range;
+    fm.cx = h_center ? h_center[0] : 0.0; fm.cy = h_center ? h_center[1] : 0.0; fm.cz = h_center ? h_center[2] : 0.0;
     for (int64_t c = 0; c < n_chunks; ++c) {
         const int64_t f0 = c * frames_per_chunk;
         const int64_t nf = (f0 + frames_per_chunk <= P) ? frames_per_chunk : P - f0;
         const int64_t n = nf * N;
+        const int64_t nb = (n + TRACE_THREADS - 1) / TRACE_THREADS;
         g.pose0 = f0;
-        if ((rc = launch_trace<MODE, false>(ctx, g, n, hp, nullptr, nullptr, stream))) return rc;
-        unsigned long long* status = (unsigned long long*)(b2 + (c & 1) * st_bytes);
-        unsigned* ticket = (unsigned*)(b2 + 2 * st_bytes + 64 * (c & 1));
-        const int64_t tiles = (n + EPI_TILE - 1) / EPI_TILE;
-        LRC_CUDA(ctx, cudaMemsetAsync(status, 0, sizeof(unsigned long long) * tiles, stream));
-        LRC_CUDA(ctx, cudaMemsetAsync(ticket, 0, sizeof(unsigned), stream));
-        EpiParams q;
-        q.hp = hp; q.n = n; q.ray0 = f0 * N; q.N = N; q.P = P;
-        q.poses = poses_for_center;
-        q.cx = h_center ? h_center[0] : 0.0; q.cy = h_center ? h_center[1] : 0.0; q.cz = h_center ? h_center[2] : 0.0;
-        q.max_range = max_range;
+        if ((rc = launch_trace<MODE, false>(ctx, g, fm, n, hp, inc, counts, nullptr, nullptr, stream))) return rc;
+        const bool last = (c == n_chunks - 1);
+        k_scan_counts<<<1, 1024, 0, stream>>>(counts, base, nb, run + c, run + c + 1, last ? out->frame_offset + P : nullptr);
+        LRC_CHECK_LAUNCH(ctx, "k_scan_counts");
+        CompactParams q;
+        q.hp = hp; q.inc = inc; q.base = base; q.run_in = run + c;
+        q.n = n; q.ray0 = f0 * N; q.N = N;
         q.labels = ctx->labels;
         q.out = *out;
+        if (!want_inc) q.out.incident_deg = nullptr;
         if (ctx->T == 0) q.out.label = nullptr;
-        q.status = status; q.ticket = ticket;
-        q.run_in = run + c; q.run_out = run + c + 1;
-        q.last = (c == n_chunks - 1);
-        k_epilogue<<<(unsigned)tiles, EPI_THREADS, 0, stream>>>(q);
-        LRC_CHECK_LAUNCH(ctx, "k_epilogue");
+        k_compact<<<(unsigned)nb, TRACE_THREADS, 0, stream>>>(q);
+        LRC_CHECK_LAUNCH(ctx, "k_compact");
     }
+    if (out->incident_deg && !want_inc)   // rays_intersect_mesh flavour: no angles are defined; keep the buffer deterministic
+        LRC_CUDA(ctx, cudaMemsetAsync(out->incident_deg, 0, sizeof(double) * (size_t)(total < out->capacity ? total : out->capacity), stream));
     return LRC_OK;
 }
 
@@ -611,7 +598,8 @@ extern "C" int lrc_cast_rays(lrc_ctx* ctx, const float* rays, int64_t N, float* 
     RayGen g;
     memset(&g, 0, sizeof g);
     g.rays = rays; g.N = 1;
-    return launch_trace<MODE_RAYS, true>(ctx, g, N, nullptr, t_hit, prim_id, (cudaStream_t)stream);
+    FrameMath fm; fm.max_range = -1.0; fm.cx = fm.cy = fm.cz = 0.0;
+    return launch_trace<MODE_RAYS, true>(ctx, g, fm, N, nullptr, nullptr, nullptr, t_hit, prim_id, (cudaStream_t)stream);
 }
 
 extern "C" int lrc_cast_rays_bruteforce(lrc_ctx* ctx, const float* rays, int64_t N, float* t_hit, uint32_t* prim_id, void* stream)
@@ -635,7 +623,7 @@ extern "C" int lrc_rays_intersect(lrc_ctx* ctx, const float* rays, int64_t N, lr
     g.rays = rays; g.N = (int)(N > 0 ? 1 : 0);
     if (N >= (int64_t)1 << 31) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_rays_intersect: N must be < 2^31 per call");
     // one frame of N rays
-    return run_scan<MODE_RAYS>(ctx, g, 1, N, nullptr, nullptr, -1.0, out, (cudaStream_t)stream);
+    return run_scan<MODE_RAYS>(ctx, g, 1, N, nullptr, -1.0, out, (cudaStream_t)stream);
 }
 
 extern "C" int lrc_scan_rays(lrc_ctx* ctx, const float* rays, int64_t N, const double* h_center, double max_range,
@@ -648,7 +636,7 @@ extern "C" int lrc_scan_rays(lrc_ctx* ctx, const float* rays, int64_t N, const d
     RayGen g;
     memset(&g, 0, sizeof g);
     g.rays = rays; g.N = 1;
-    return run_scan<MODE_RAYS>(ctx, g, 1, N, nullptr, h_center, max_range, out, (cudaStream_t)stream);
+    return run_scan<MODE_RAYS>(ctx, g, 1, N, h_center, max_range, out, (cudaStream_t)stream);
 }
 
 extern "C" int lrc_scan_single_axis(lrc_ctx* ctx, const double* poses, int64_t P, const lrc_single_axis* s,
@@ -660,7 +648,7 @@ extern "C" int lrc_scan_single_axis(lrc_ctx* ctx, const double* poses, int64_t P
     RayGen g;
     if ((rc = fill_single(ctx, s, poses, g, (cudaStream_t)stream))) return rc;
     fill_noise(nz, g, false);
-    return run_scan<MODE_SINGLE>(ctx, g, P, g.N, poses, nullptr, s->max_range, out, (cudaStream_t)stream);
+    return run_scan<MODE_SINGLE>(ctx, g, P, g.N, nullptr, s->max_range, out, (cudaStream_t)stream);
 }
 
 extern "C" int lrc_scan_dual_axis(lrc_ctx* ctx, const double* poses, int64_t P, const lrc_dual_axis* s,
@@ -672,7 +660,7 @@ extern "C" int lrc_scan_dual_axis(lrc_ctx* ctx, const double* poses, int64_t P, 
     RayGen g;
     if ((rc = fill_dual(ctx, s, poses, g))) return rc;
     fill_noise(nz, g, true);
-    return run_scan<MODE_DUAL>(ctx, g, P, g.N, poses, nullptr, s->max_range, out, (cudaStream_t)stream);
+    return run_scan<MODE_DUAL>(ctx, g, P, g.N, nullptr, s->max_range, out, (cudaStream_t)stream);
 }
 
 extern "C" int lrc_gen_rays_single_axis(lrc_ctx* ctx, const double* poses, int64_t P, const lrc_single_axis* s,
