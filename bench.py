@@ -382,21 +382,14 @@ def run_ours(args):
     pinned_pose = torch.from_numpy(np.ascontiguousarray(poses.reshape(-1, 16))).pin_memory()
     pv, pf, pl = (torch.from_numpy(verts).pin_memory(), torch.from_numpy(tris).pin_memory(),
                   torch.from_numpy(labels.view(np.int32)).pin_memory())
-    cap = P * n_frame
-    h_xyz = torch.empty((cap, 3), dtype=torch.float32).pin_memory()
-    h_inc = torch.empty(cap, dtype=torch.float64).pin_memory()
-    h_lab = torch.empty(cap, dtype=torch.int32).pin_memory()
+    host = ctx.alloc_host_buffers(P * n_frame, P, labels=True)
 
     def e2e_step():
-        ctx.set_mesh_arrays(pv.to(dev, non_blocking=True), pf.to(dev, non_blocking=True), pl.to(dev, non_blocking=True))
-        pd = pinned_pose.to(dev, non_blocking=True)
-        ctx.scan_enqueue(pd, intr, noise, bufs)
-        m = int(bufs["off"][-1].item())                    # D2H of the count (synchronises)
-        h_xyz[:m].copy_(bufs["xyz"][:m], non_blocking=True)
-        h_inc[:m].copy_(bufs["incident"][:m], non_blocking=True)
-        h_lab[:m].copy_(bufs["label"][:m], non_blocking=True)
-        torch.cuda.synchronize()
-        return m
+        # mesh H2D + LBVH build (the reference rebuilds its scene on every frame; here once per trajectory) ...
+        ctx.set_mesh_host(pv, pf, pl)
+        # ... then the trajectory: poses H2D from pinned memory, chunked scan, D2H pipelined behind later chunks
+        res = ctx.scan_to_host(pinned_pose, intr, noise, host=host, chunk_poses=args.e2e_chunk)
+        return res["num_points"]
 
     for _ in range(2):
         m = e2e_step()
@@ -454,6 +447,7 @@ def main():
     ap.add_argument("--tris", type=int, default=None, help="override the triangle count (debugging)")
     ap.add_argument("--poses", type=int, default=None, help="override poses per GPU (debugging)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--e2e-chunk", type=int, default=None, help="poses per chunk of the pipelined e2e path")
     ap.add_argument("--variant", type=int, default=None, help="traversal kernel variant (lrc_set_option)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--ref-frames", type=int, default=2, help="--impl reference: frames per step")

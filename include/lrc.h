@@ -152,6 +152,21 @@ int lrc_scan_single_axis(lrc_ctx* ctx, const double* poses, int64_t P, const lrc
 int lrc_scan_dual_axis(lrc_ctx* ctx, const double* poses, int64_t P, const lrc_dual_axis* h_sensor,
                        const lrc_noise* h_noise, lrc_out* out, void* stream);
 
+/* ---- the same, with HOST buffers (the reference-facing call: numpy in, numpy out) -------------- */
+/* h_poses: P x 16 float64 on the host.  h_out: an lrc_out whose pointers are HOST memory (page-locked memory makes
+ * the copies asynchronous; pageable memory works, slower).  The trajectory is cut into chunks of `chunk_poses` poses
+ * (0 = automatic); every chunk's kernels are enqueued at once on an internal stream and each chunk's compacted
+ * records are copied back on a second stream as soon as that chunk is finished, so the PCIe transfer overlaps the
+ * traversal of later chunks.  Synchronous: on return every output is on the host and *h_num_points is set.
+ * These two calls do NOT use the caller's stream. */
+int lrc_scan_single_axis_host(lrc_ctx* ctx, const double* h_poses, int64_t P, const lrc_single_axis* h_sensor,
+                              const lrc_noise* h_noise, lrc_out* h_out, int64_t chunk_poses, int64_t* h_num_points);
+int lrc_scan_dual_axis_host(lrc_ctx* ctx, const double* h_poses, int64_t P, const lrc_dual_axis* h_sensor,
+                            const lrc_noise* h_noise, lrc_out* h_out, int64_t chunk_poses, int64_t* h_num_points);
+/* == lrc_set_mesh with HOST arrays (uploads, then builds; synchronous). */
+int lrc_set_mesh_host(lrc_ctx* ctx, const float* h_verts, int64_t V, const int32_t* h_tris, int64_t T,
+                      const uint32_t* h_tri_label);
+
 /* ---- get_rays ------------------------------------------------------------------------------- */
 /* == IndoorLidar.get_rays (indoor_lidar.py:27-53): rays H*W x 6 float32, index j*W + i. */
 int lrc_gen_rays_single_axis(lrc_ctx* ctx, const double* poses, int64_t P, const lrc_single_axis* h_sensor,

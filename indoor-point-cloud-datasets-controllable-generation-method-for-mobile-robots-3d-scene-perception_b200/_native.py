@@ -70,6 +70,9 @@ SYMBOLS = {
     "lrc_scan_rays": (_i32, [_vp, _vp, _i64, C.POINTER(_dbl), _dbl, C.POINTER(Out), _vp]),
     "lrc_scan_single_axis": (_i32, [_vp, _vp, _i64, C.POINTER(SingleAxis), C.POINTER(Noise), C.POINTER(Out), _vp]),
     "lrc_scan_dual_axis": (_i32, [_vp, _vp, _i64, C.POINTER(DualAxis), C.POINTER(Noise), C.POINTER(Out), _vp]),
+    "lrc_scan_single_axis_host": (_i32, [_vp, _vp, _i64, C.POINTER(SingleAxis), C.POINTER(Noise), C.POINTER(Out), _i64, C.POINTER(_i64)]),
+    "lrc_scan_dual_axis_host": (_i32, [_vp, _vp, _i64, C.POINTER(DualAxis), C.POINTER(Noise), C.POINTER(Out), _i64, C.POINTER(_i64)]),
+    "lrc_set_mesh_host": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp]),
     "lrc_gen_rays_single_axis": (_i32, [_vp, _vp, _i64, C.POINTER(SingleAxis), _vp, _vp]),
     "lrc_gen_rays_dual_axis": (_i32, [_vp, _vp, _i64, C.POINTER(DualAxis), C.POINTER(Noise), _vp, _vp, _vp]),
     "lrc_set_counting": (_i32, [_vp, _i32]),

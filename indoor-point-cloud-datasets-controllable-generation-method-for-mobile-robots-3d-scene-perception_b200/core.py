@@ -365,6 +365,77 @@ class Context:
             bufs, _ = self.scan_enqueue(p, intr, noise)
             return self._finish(bufs)
 
+    # ---- trajectory scan with HOST results: chunked, D2H overlapped with the next chunks' kernels ----
+    def alloc_host_buffers(self, capacity: int, frames: int, labels: bool = True, extras: bool = False) -> dict:
+        """Pinned host staging for ``scan_to_host`` (allocate once, reuse across calls)."""
+        cap = max(1, int(capacity))
+        h = {
+            "points": torch.empty((cap, 3), dtype=torch.float32).pin_memory(),
+            "incident": torch.empty(cap, dtype=torch.float64).pin_memory(),
+            "label": torch.empty(cap, dtype=torch.int32).pin_memory() if labels else None,
+            "prim_id": torch.empty(cap, dtype=torch.int32).pin_memory() if extras else None,
+            "ray_idx": torch.empty(cap, dtype=torch.int32).pin_memory() if extras else None,
+            "frame_offset": torch.zeros(frames + 1, dtype=torch.int64).pin_memory(),
+        }
+        return h
+
+    def scan_to_host(self, poses, intr, noise: Optional[NoiseConfig] = None, host: Optional[dict] = None,
+                     chunk_poses: Optional[int] = None) -> dict:
+        """``scan`` for callers that want numpy (``lrc_scan_*_host``): poses come from host memory, the trajectory is
+        cut into pose chunks whose kernels are all enqueued up front, and each chunk's compacted records are copied
+        into (pinned) host memory on a second stream as soon as that chunk is done -- the PCIe transfer, 24 B per
+        point and the end-to-end bottleneck, overlaps the remaining chunks' traversal.  Synchronous."""
+        poses_h = np.ascontiguousarray(poses.numpy() if isinstance(poses, torch.Tensor) else poses, dtype=np.float64).reshape(-1, 16)
+        P = int(poses_h.shape[0])
+        n_frame = rays_per_frame(intr)
+        if host is None:
+            host = self.alloc_host_buffers(P * n_frame, P)
+        if host["points"].shape[0] < max(1, P * n_frame) or host["frame_offset"].shape[0] < P + 1:
+            raise ValueError("host buffers are too small for this trajectory")
+
+        def hp(name):
+            t = host.get(name)
+            return None if t is None else C.c_void_p(t.data_ptr())
+
+        out = nat.Out(hp("points"), hp("incident"), hp("prim_id"), hp("label"), hp("ray_idx"), hp("frame_offset"),
+                      int(host["points"].shape[0]))
+        nz = noise.struct() if noise is not None else None
+        nzp = C.byref(nz) if nz is not None else None
+        total = C.c_int64(0)
+        chunk = 0 if chunk_poses is None else int(chunk_poses)
+        pp = C.c_void_p(poses_h.ctypes.data)
+        with torch.cuda.device(self.device):
+            if is_dual_axis(intr):
+                d = dual_axis_desc(intr)
+                nat.check(self._h, self._lib.lrc_scan_dual_axis_host(self._h, pp, P, C.byref(d), nzp, C.byref(out), chunk, C.byref(total)))
+            else:
+                d = single_axis_desc(intr)
+                nat.check(self._h, self._lib.lrc_scan_single_axis_host(self._h, pp, P, C.byref(d), nzp, C.byref(out), chunk, C.byref(total)))
+        m = int(total.value)
+        res = {"points": host["points"][:m].numpy(), "incident": host["incident"][:m].numpy(),
+               "frame_offset": host["frame_offset"][:P + 1].numpy(), "num_points": m}
+        for k in ("label", "prim_id", "ray_idx"):
+            if host.get(k) is not None:
+                res[k] = host[k][:m].numpy().view(np.uint32)
+        return res
+
+    def set_mesh_host(self, verts: np.ndarray, tris: np.ndarray, labels: Optional[np.ndarray] = None) -> None:
+        """``lrc_set_mesh_host``: upload float32 vertices / int32 indices / uint32 labels from host memory (pinned
+        tensors or numpy arrays) and build the LBVH.  Synchronous."""
+        def as_np(a, dt):
+            if isinstance(a, torch.Tensor):
+                a = a.numpy()
+            return np.ascontiguousarray(a, dtype=dt)
+        v = as_np(verts, np.float32).reshape(-1, 3)
+        f = as_np(tris, np.int32).reshape(-1, 3)
+        lab = None if labels is None else as_np(labels, np.int32 if (isinstance(labels, torch.Tensor) or labels.dtype == np.int32) else np.uint32).reshape(-1)
+        with torch.cuda.device(self.device):
+            nat.check(self._h, self._lib.lrc_set_mesh_host(self._h, C.c_void_p(v.ctypes.data), v.shape[0], C.c_void_p(f.ctypes.data), f.shape[0],
+                                                           None if lab is None else C.c_void_p(lab.ctypes.data)))
+        self.num_tris = int(f.shape[0])
+        self.has_labels = lab is not None
+        self._mesh_key = None
+
     # ---- get_rays ----
     def gen_rays(self, poses, intr, noise: Optional[NoiseConfig] = None):
         """-> (rays (P*N,6) float32 tensor, keep (P*N,) uint8 tensor | None)."""

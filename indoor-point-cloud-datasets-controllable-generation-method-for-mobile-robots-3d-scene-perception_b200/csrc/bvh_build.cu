@@ -2,7 +2,7 @@
 //     o3d.t.geometry.RaycastingScene() + add_triangles(...)   (reference raycast_engine_cpu.py:46-47)
 //
 // Pipeline (all on the caller's stream, one synchronisation at the end to read back tree depth):
-//   k_scene_bounds   vertex-index validation + scene AABB (warp shuffles + ordered-int atomics)
+//   k_vertex_bounds, k_check_indices   scene AABB (warp shuffles + ordered-int atomics), index validation
 //   k_morton         63-bit Morton code of each triangle's box centre (cubic cells, 21 bits/axis)
 //   radix sort       hand-written LSD sort of (u64 key, u32 triangle id), 8 bits x 8 passes:
 //                    k_rs_hist -> k_rs_scan -> k_rs_scatter (stable multi-split by warp match)
@@ -29,7 +29,6 @@ struct BuildMeta {            // lives in device memory during a build
     unsigned lo[3], hi[3];    // ordered-uint encoded scene bounds
     int bad_index;            // set when a triangle references a vertex outside [0, V)
     int height;               // tree height (edges on the longest root->leaf path)
-    double area_sum;          // sum of internal-node surface areas (for the SAH diagnostic)
     float root_lo[3], root_hi[3];
 };
 
@@ -38,32 +37,23 @@ __global__ void k_meta_init(BuildMeta* m)
     for (int k = 0; k < 3; ++k) { m->lo[k] = 0xffffffffu; m->hi[k] = 0u; }
     m->bad_index = 0;
     m->height = 0;
-    m->area_sum = 0.0;
 }
 
-__global__ void k_scene_bounds(const float* __restrict__ verts, int64_t V, const int32_t* __restrict__ tris, int64_t T,
-                               BuildMeta* meta)
+// scene AABB over the vertex array (coalesced; a vertex no triangle references still counts -- harmless for the
+// Morton normalisation and the pad) ...
+__global__ void k_vertex_bounds(const float* __restrict__ verts, int64_t V, BuildMeta* meta)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float lo[3] = {LRC_INF, LRC_INF, LRC_INF}, hi[3] = {-LRC_INF, -LRC_INF, -LRC_INF};
-    bool bad = false;
-    if (i < T) {
+    if (i < V) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            int64_t v = tris[3 * i + c];
-            if (v < 0 || v >= V) { bad = true; continue; }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                float x = verts[3 * v + k];
-                lo[k] = fminf(lo[k], x);
-                hi[k] = fmaxf(hi[k], x);
-            }
-        }
+        for (int k = 0; k < 3; ++k) lo[k] = hi[k] = verts[3 * i + k];
     }
-    if (__any_sync(0xffffffffu, bad) && bad) atomicExch(&meta->bad_index, 1);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         float l = lo[k], h = hi[k];
+        // a NaN coordinate must not vanish inside fminf/fmaxf: turn it into +inf so the finiteness check fires
+        if (l != l) { l = LRC_INF; h = LRC_INF; }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o));
@@ -74,6 +64,18 @@ __global__ void k_scene_bounds(const float* __restrict__ verts, int64_t V, const
             atomicMax(&meta->hi[k], f2ord(h));
         }
     }
+}
+
+// ... and index validation over the 3T indices (coalesced)
+__global__ void k_check_indices(const int32_t* __restrict__ tris, int64_t n3, int64_t V, BuildMeta* meta)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool bad = false;
+    if (i < n3) {
+        int64_t v = tris[i];
+        bad = v < 0 || v >= V;
+    }
+    if (__any_sync(0xffffffffu, bad) && lane_id() == 0) atomicExch(&meta->bad_index, 1);
 }
 
 __device__ __forceinline__ uint64_t expand21(uint32_t v)
@@ -148,15 +150,19 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t* __restri
 
 __global__ void __launch_bounds__(1024) k_rs_scan(unsigned* __restrict__ a, int64_t M)
 {
+    // exclusive scan of M counters by one block, 4 per thread per trip (M = 256 * number of sort tiles)
     __shared__ unsigned warp_sums[32];
     __shared__ unsigned carry;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry = 0u;
     __syncthreads();
-    for (int64_t base = 0; base < M; base += 1024) {
-        int64_t idx = base + threadIdx.x;
-        unsigned v = idx < M ? a[idx] : 0u;
-        unsigned incl = v;
+    for (int64_t base = 0; base < M; base += 4096) {
+        const int64_t idx = base + 4 * (int64_t)threadIdx.x;
+        unsigned v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = idx + k < M ? a[idx + k] : 0u;
+        const unsigned mine = v[0] + v[1] + v[2] + v[3];
+        unsigned incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -165,19 +171,23 @@ __global__ void __launch_bounds__(1024) k_rs_scan(unsigned* __restrict__ a, int6
         if (lane == 31) warp_sums[w] = incl;
         __syncthreads();
         if (w == 0) {
-            unsigned s = warp_sums[lane], si = s;
+            unsigned sv = warp_sums[lane], si = sv;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 unsigned t = __shfl_up_sync(0xffffffffu, si, o);
                 if (lane >= o) si += t;
             }
-            warp_sums[lane] = si - s;
+            warp_sums[lane] = si - sv;
         }
         __syncthreads();
-        unsigned excl = incl - v + warp_sums[w] + carry;
-        if (idx < M) a[idx] = excl;
+        unsigned run = incl - mine + warp_sums[w] + carry;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (idx + k < M) a[idx + k] = run;
+            run += v[k];
+        }
         __syncthreads();
-        if (threadIdx.x == 1023) carry = excl + v;
+        if (threadIdx.x == 1023) carry = run;
         __syncthreads();
     }
 }
@@ -333,8 +343,6 @@ __global__ void k_refit(int n, const int* __restrict__ parent_leaf, const int* _
         node_lo[cur] = lo;
         node_hi[cur] = hi;
         write_node(nodes_out + 4 * (int64_t)cur, l0, h0, l1, h1, ch.x, ch.y);
-        float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z;
-        atomicAdd(&meta->area_sum, (double)(2.f * (ex * ey + ey * ez + ez * ex)));
         int up = parent_node[cur];
         if (up < 0) {
             meta->height = (int)height;
@@ -352,10 +360,22 @@ __global__ void k_single_leaf_root(const float4* leaf_lo, const float4* leaf_hi,
     float4 l = leaf_lo[0], h = leaf_hi[0];
     write_node(nodes_out, l, h, l, h, ~0, ~0);
     meta->height = 1;
-    float ex = h.x - l.x, ey = h.y - l.y, ez = h.z - l.z;
-    meta->area_sum = 2.0 * (ex * ey + ey * ez + ez * ex);
     meta->root_lo[0] = l.x; meta->root_lo[1] = l.y; meta->root_lo[2] = l.z;
     meta->root_hi[0] = h.x; meta->root_hi[1] = h.y; meta->root_hi[2] = h.z;
+}
+
+// SAH diagnostic: sum of the surface areas of every child box stored in the node records
+__global__ void k_sah_sum(const float4* __restrict__ nodes, int64_t n_nodes, double* out)
+{
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_nodes; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 n0 = nodes[4 * i], n1 = nodes[4 * i + 1], n2 = nodes[4 * i + 2];
+        acc += 8.0 * ((double)n0.w * n1.x + (double)n1.x * n1.y + (double)n1.y * n0.w);   // child 0: h = (n0.w, n1.x, n1.y)
+        acc += 8.0 * ((double)n2.y * n2.z + (double)n2.z * n2.w + (double)n2.w * n2.y);   // child 1: h = (n2.y, n2.z, n2.w)
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane_id() == 0) atomicAdd(out, acc);
 }
 
 }  // namespace
@@ -428,8 +448,10 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
     const unsigned gT = (unsigned)((T + TB - 1) / TB);
     k_meta_init<<<1, 1, 0, stream>>>(meta);
     LRC_CHECK_LAUNCH(ctx, "k_meta_init");
-    k_scene_bounds<<<gT, TB, 0, stream>>>(verts, V, tris, T, meta);
-    LRC_CHECK_LAUNCH(ctx, "k_scene_bounds");
+    k_vertex_bounds<<<(unsigned)((V + TB - 1) / TB), TB, 0, stream>>>(verts, V, meta);
+    LRC_CHECK_LAUNCH(ctx, "k_vertex_bounds");
+    k_check_indices<<<(unsigned)((3 * T + TB - 1) / TB), TB, 0, stream>>>(tris, 3 * T, V, meta);
+    LRC_CHECK_LAUNCH(ctx, "k_check_indices");
 
     BuildMeta hm;
     LRC_CUDA(ctx, cudaMemcpyAsync(&hm, meta, sizeof hm, cudaMemcpyDeviceToHost, stream));
@@ -492,8 +514,8 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
     inf.box_pad = pad;
     {
         float ex = hm.root_hi[0] - hm.root_lo[0], ey = hm.root_hi[1] - hm.root_lo[1], ez = hm.root_hi[2] - hm.root_lo[2];
-        double root_area = 2.0 * ((double)ex * ey + (double)ey * ez + (double)ez * ex);
-        inf.sah_cost = root_area > 0 ? (float)(hm.area_sum / root_area) : 0.f;
+        ctx->root_area = 2.0 * ((double)ex * ey + (double)ey * ez + (double)ez * ex);
+        inf.sah_cost = -1.f;   // computed on demand by lrc_bvh_get_info
     }
     inf.bytes_nodes = (int64_t)sizeof(float4) * 4 * n_nodes;
     inf.bytes_tris = (int64_t)sizeof(float4) * 3 * T;
@@ -510,6 +532,19 @@ extern "C" int lrc_bvh_get_info(lrc_ctx* ctx, lrc_bvh_info* h_info)
 {
     if (!ctx || !h_info) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_bvh_get_info: NULL argument");
     if (!ctx->has_mesh) return lrc_fail(ctx, LRC_ERR_NO_MESH, "lrc_bvh_get_info: no mesh set");
+    if (ctx->info.sah_cost < 0.f && ctx->T > 0) {
+        // SAH cost = (area(root) + sum of all child-box areas) / area(root), C_traverse = C_intersect = 1
+        LRC_CUDA(ctx, cudaSetDevice(ctx->device));
+        double* d_sum = nullptr;
+        LRC_CUDA(ctx, cudaMalloc((void**)&d_sum, sizeof(double)));
+        LRC_CUDA(ctx, cudaMemset(d_sum, 0, sizeof(double)));
+        k_sah_sum<<<296, 256>>>(ctx->nodes, ctx->info.num_nodes, d_sum);
+        LRC_CHECK_LAUNCH(ctx, "k_sah_sum");
+        double h_sum = 0.0;
+        LRC_CUDA(ctx, cudaMemcpy(&h_sum, d_sum, sizeof(double), cudaMemcpyDeviceToHost));
+        LRC_CUDA(ctx, cudaFree(d_sum));
+        ctx->info.sah_cost = ctx->root_area > 0 ? (float)((ctx->root_area + h_sum) / ctx->root_area) : 0.f;
+    }
     *h_info = ctx->info;
     return LRC_OK;
 }

@@ -26,14 +26,27 @@ struct lrc_ctx {
     uint32_t* labels = nullptr;   // T, original triangle order
     size_t nodes_cap = 0, tris_cap = 0, labels_cap = 0;   // in elements
     lrc_bvh_info info = {};
+    double root_area = 0.0;
 
     // ---- grow-only scratch ----
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    cudaEvent_t scratch_event = nullptr;   // recorded after the last scan that used the scratch
     void* scratch2 = nullptr;     // scan bookkeeping (tile status words, ticket, running total)
     size_t scratch2_bytes = 0;
     double* tables = nullptr;     // ray-generation tables
     size_t tables_bytes = 0;
+
+    // ---- host-buffer entry points (lrc_*_host): internal streams, staging, device outputs ----
+    cudaStream_t s_compute = nullptr, s_copy = nullptr, s_count = nullptr;
+    void* host_dev = nullptr;          // device-side lrc_out arrays + poses for a whole trajectory
+    size_t host_dev_bytes = 0;
+    int64_t* h_stage = nullptr;        // page-locked frame-offset staging
+    size_t h_stage_elems = 0;
+    cudaEvent_t* events = nullptr;     // 2 per chunk
+    size_t n_events = 0;
+    void* mesh_dev = nullptr;          // device copies of host mesh arrays (lrc_set_mesh_host)
+    size_t mesh_dev_bytes = 0;
 
     // ---- measurement ----
     unsigned long long* d_counters = nullptr;   // rays, nodes, tris, hits

@@ -424,6 +424,9 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
     const size_t hp_bytes = align_up(sizeof(float4) * (size_t)chunk_rays, 256);
     const size_t inc_bytes = want_inc ? align_up(sizeof(double) * (size_t)chunk_rays, 256) : 0;
     if ((rc = lrc_grow(ctx, &ctx->scratch, &ctx->scratch_bytes, hp_bytes + inc_bytes))) return rc;
+    // the scratch is shared by every scan of this context: order this call after the previous one, whatever its stream
+    if (!ctx->scratch_event) LRC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->scratch_event, cudaEventDisableTiming));
+    else LRC_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->scratch_event, 0));
     const size_t cnt_bytes = align_up(sizeof(unsigned) * (size_t)max_blocks, 256);
     const size_t need2 = 2 * cnt_bytes + sizeof(long long) * (size_t)(n_chunks + 1);
     if ((rc = lrc_grow(ctx, &ctx->scratch2, &ctx->scratch2_bytes, need2))) return rc;
@@ -457,6 +460,7 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
         k_compact<<<(unsigned)nb, TRACE_THREADS, 0, stream>>>(q);
         LRC_CHECK_LAUNCH(ctx, "k_compact");
     }
+    LRC_CUDA(ctx, cudaEventRecord(ctx->scratch_event, stream));
     if (out->incident_deg && !want_inc)   // rays_intersect_mesh flavour: no angles are defined; keep the buffer deterministic
         LRC_CUDA(ctx, cudaMemsetAsync(out->incident_deg, 0, sizeof(double) * (size_t)(total < out->capacity ? total : out->capacity), stream));
     return LRC_OK;
@@ -549,6 +553,14 @@ extern "C" void lrc_destroy(lrc_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaFree(ctx->nodes); cudaFree(ctx->tris); cudaFree(ctx->labels);
     cudaFree(ctx->scratch); cudaFree(ctx->scratch2); cudaFree(ctx->tables); cudaFree(ctx->d_counters);
+    cudaFree(ctx->host_dev); cudaFree(ctx->mesh_dev);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->scratch_event) cudaEventDestroy(ctx->scratch_event);
+    for (size_t i = 0; i < ctx->n_events; ++i) cudaEventDestroy(ctx->events[i]);
+    free(ctx->events);
+    if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
+    if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
+    if (ctx->s_count) cudaStreamDestroy(ctx->s_count);
     delete ctx;
 }
 
@@ -694,4 +706,169 @@ extern "C" int lrc_gen_rays_dual_axis(lrc_ctx* ctx, const double* poses, int64_t
     k_gen_rays<MODE_DUAL><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, n, rays, keep);
     LRC_CHECK_LAUNCH(ctx, "k_gen_rays");
     return LRC_OK;
+}
+
+// ======================================================================================================
+// Host-buffer entry points: chunked scan with the device-to-host copies pipelined behind later chunks.
+namespace {
+
+int ensure_host_plumbing(lrc_ctx* ctx, size_t n_chunks, int64_t P)
+{
+    if (!ctx->s_compute) {
+        LRC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));
+        LRC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
+        LRC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_count, cudaStreamNonBlocking));
+    }
+    if (ctx->n_events < 2 * n_chunks) {
+        cudaEvent_t* ev = (cudaEvent_t*)realloc(ctx->events, sizeof(cudaEvent_t) * 2 * n_chunks);
+        if (!ev) return lrc_fail(ctx, LRC_ERR_CUDA, "out of host memory for events");
+        ctx->events = ev;
+        for (size_t i = ctx->n_events; i < 2 * n_chunks; ++i) LRC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->events[i], cudaEventDisableTiming));
+        ctx->n_events = 2 * n_chunks;
+    }
+    const size_t need = (size_t)P + n_chunks + 8;
+    if (ctx->h_stage_elems < need) {
+        if (ctx->h_stage) LRC_CUDA(ctx, cudaFreeHost(ctx->h_stage));
+        ctx->h_stage = nullptr; ctx->h_stage_elems = 0;
+        LRC_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_stage, sizeof(int64_t) * need, cudaHostAllocDefault));
+        ctx->h_stage_elems = need;
+    }
+    return LRC_OK;
+}
+
+template <int MODE>
+int run_scan_host(lrc_ctx* ctx, RayGen g, const double* h_poses, int64_t P, int64_t N, double max_range, lrc_out* h_out,
+                  int64_t chunk_poses, int64_t* h_num_points)
+{
+    if (!h_out || !h_out->xyz || !h_out->frame_offset || !h_num_points)
+        return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_scan_*_host: xyz, frame_offset and h_num_points are required");
+    if (h_out->capacity < P * N) return lrc_fail(ctx, LRC_ERR_CAPACITY, "lrc_scan_*_host: capacity is smaller than the number of rays");
+    *h_num_points = 0;
+    h_out->frame_offset[0] = 0;
+    if (P == 0) return LRC_OK;
+    if (chunk_poses <= 0) {
+        chunk_poses = (int64_t)(1 << 20) / N;                  // ~1M rays (~24-32 MB of records) per chunk
+        if (chunk_poses < 1) chunk_poses = 1;
+    }
+    if (chunk_poses > P) chunk_poses = P;
+    const size_t n_chunks = (size_t)((P + chunk_poses - 1) / chunk_poses);
+    int rc = ensure_host_plumbing(ctx, n_chunks, P);
+    if (rc) return rc;
+    // device image of the whole trajectory's outputs: [poses | xyz | incident | prim | label | ray | frame offsets]
+    const size_t cap = (size_t)(P * N);
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_pose = carve(sizeof(double) * 16 * (size_t)P);
+    const size_t o_xyz = carve(sizeof(float) * 3 * cap);
+    const size_t o_inc = h_out->incident_deg ? carve(sizeof(double) * cap) : 0;
+    const size_t o_prim = h_out->prim_id ? carve(sizeof(uint32_t) * cap) : 0;
+    const size_t o_lab = h_out->label ? carve(sizeof(uint32_t) * cap) : 0;
+    const size_t o_ray = h_out->ray_idx ? carve(sizeof(uint32_t) * cap) : 0;
+    const size_t o_off = carve(sizeof(int64_t) * ((size_t)P + n_chunks));
+    if ((rc = lrc_grow(ctx, &ctx->host_dev, &ctx->host_dev_bytes, off))) return rc;
+    char* base = (char*)ctx->host_dev;
+    double* d_poses = (double*)(base + o_pose);
+    LRC_CUDA(ctx, cudaMemcpyAsync(d_poses, h_poses, sizeof(double) * 16 * (size_t)P, cudaMemcpyHostToDevice, ctx->s_compute));
+    g.poses = d_poses;
+    const uint64_t pose_base = g.pose_index_base;
+    // 1) enqueue every chunk's kernels; a tiny copy of each chunk's frame offsets follows on its own stream
+    for (size_t c = 0; c < n_chunks; ++c) {
+        const int64_t f0 = (int64_t)c * chunk_poses;
+        const int64_t nf = f0 + chunk_poses <= P ? chunk_poses : P - f0;
+        lrc_out d;
+        d.xyz = (float*)(base + o_xyz) + 3 * (size_t)(f0 * N);
+        d.incident_deg = h_out->incident_deg ? (double*)(base + o_inc) + (size_t)(f0 * N) : nullptr;
+        d.prim_id = h_out->prim_id ? (uint32_t*)(base + o_prim) + (size_t)(f0 * N) : nullptr;
+        d.label = h_out->label ? (uint32_t*)(base + o_lab) + (size_t)(f0 * N) : nullptr;
+        d.ray_idx = h_out->ray_idx ? (uint32_t*)(base + o_ray) + (size_t)(f0 * N) : nullptr;
+        d.frame_offset = (int64_t*)(base + o_off) + f0 + (int64_t)c;     // nf + 1 entries per chunk
+        d.capacity = nf * N;
+        RayGen gc = g;
+        gc.poses = d_poses + 16 * f0;
+        gc.pose_index_base = pose_base + (uint64_t)f0;
+        if ((rc = run_scan<MODE>(ctx, gc, nf, N, nullptr, max_range, &d, ctx->s_compute))) return rc;
+        LRC_CUDA(ctx, cudaEventRecord(ctx->events[2 * c], ctx->s_compute));
+        LRC_CUDA(ctx, cudaStreamWaitEvent(ctx->s_count, ctx->events[2 * c], 0));
+        LRC_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage + f0 + (int64_t)c, d.frame_offset, sizeof(int64_t) * (size_t)(nf + 1),
+                                      cudaMemcpyDeviceToHost, ctx->s_count));
+        LRC_CUDA(ctx, cudaEventRecord(ctx->events[2 * c + 1], ctx->s_count));
+    }
+    // 2) as each chunk's counts arrive, enqueue exactly-sized record copies on the copy stream
+    int64_t total = 0;
+    for (size_t c = 0; c < n_chunks; ++c) {
+        const int64_t f0 = (int64_t)c * chunk_poses;
+        const int64_t nf = f0 + chunk_poses <= P ? chunk_poses : P - f0;
+        LRC_CUDA(ctx, cudaEventSynchronize(ctx->events[2 * c + 1]));
+        const int64_t* st = ctx->h_stage + f0 + (int64_t)c;
+        const int64_t m = st[nf];
+        for (int64_t k = 0; k <= nf; ++k) h_out->frame_offset[f0 + k] = total + st[k];
+        if (m > 0) {
+            const size_t src = (size_t)(f0 * N);
+            LRC_CUDA(ctx, cudaStreamWaitEvent(ctx->s_copy, ctx->events[2 * c], 0));
+            LRC_CUDA(ctx, cudaMemcpyAsync(h_out->xyz + 3 * total, (float*)(base + o_xyz) + 3 * src, sizeof(float) * 3 * (size_t)m, cudaMemcpyDeviceToHost, ctx->s_copy));
+            if (h_out->incident_deg)
+                LRC_CUDA(ctx, cudaMemcpyAsync(h_out->incident_deg + total, (double*)(base + o_inc) + src, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, ctx->s_copy));
+            if (h_out->label)
+                LRC_CUDA(ctx, cudaMemcpyAsync(h_out->label + total, (uint32_t*)(base + o_lab) + src, sizeof(uint32_t) * (size_t)m, cudaMemcpyDeviceToHost, ctx->s_copy));
+            if (h_out->prim_id)
+                LRC_CUDA(ctx, cudaMemcpyAsync(h_out->prim_id + total, (uint32_t*)(base + o_prim) + src, sizeof(uint32_t) * (size_t)m, cudaMemcpyDeviceToHost, ctx->s_copy));
+            if (h_out->ray_idx)
+                LRC_CUDA(ctx, cudaMemcpyAsync(h_out->ray_idx + total, (uint32_t*)(base + o_ray) + src, sizeof(uint32_t) * (size_t)m, cudaMemcpyDeviceToHost, ctx->s_copy));
+        }
+        total += m;
+    }
+    LRC_CUDA(ctx, cudaStreamSynchronize(ctx->s_copy));
+    LRC_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
+    *h_num_points = total;
+    return LRC_OK;
+}
+
+}  // namespace
+
+extern "C" int lrc_scan_single_axis_host(lrc_ctx* ctx, const double* h_poses, int64_t P, const lrc_single_axis* s,
+                                         const lrc_noise* nz, lrc_out* h_out, int64_t chunk_poses, int64_t* h_num_points)
+{
+    int rc = precheck(ctx, "lrc_scan_single_axis_host");
+    if (rc) return rc;
+    if (P < 0 || (P > 0 && !h_poses)) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_scan_single_axis_host: bad poses");
+    if ((rc = ensure_host_plumbing(ctx, 1, P > 0 ? P : 1))) return rc;
+    RayGen g;
+    if ((rc = fill_single(ctx, s, nullptr, g, ctx->s_compute))) return rc;
+    fill_noise(nz, g, false);
+    return run_scan_host<MODE_SINGLE>(ctx, g, h_poses, P, g.N, s->max_range, h_out, chunk_poses, h_num_points);
+}
+
+extern "C" int lrc_scan_dual_axis_host(lrc_ctx* ctx, const double* h_poses, int64_t P, const lrc_dual_axis* s,
+                                       const lrc_noise* nz, lrc_out* h_out, int64_t chunk_poses, int64_t* h_num_points)
+{
+    int rc = precheck(ctx, "lrc_scan_dual_axis_host");
+    if (rc) return rc;
+    if (P < 0 || (P > 0 && !h_poses)) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_scan_dual_axis_host: bad poses");
+    if ((rc = ensure_host_plumbing(ctx, 1, P > 0 ? P : 1))) return rc;
+    RayGen g;
+    if ((rc = fill_dual(ctx, s, nullptr, g))) return rc;
+    fill_noise(nz, g, true);
+    return run_scan_host<MODE_DUAL>(ctx, g, h_poses, P, g.N, s->max_range, h_out, chunk_poses, h_num_points);
+}
+
+extern "C" int lrc_set_mesh_host(lrc_ctx* ctx, const float* h_verts, int64_t V, const int32_t* h_tris, int64_t T,
+                                 const uint32_t* h_tri_label)
+{
+    if (!ctx) return lrc_fail(nullptr, LRC_ERR_INVALID, "lrc_set_mesh_host: ctx is NULL");
+    if (V < 0 || T < 0 || (T > 0 && (!h_verts || !h_tris))) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_mesh_host: bad arguments");
+    LRC_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure_host_plumbing(ctx, 1, 1);
+    if (rc) return rc;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_v = carve(sizeof(float) * 3 * (size_t)V), o_t = carve(sizeof(int32_t) * 3 * (size_t)T);
+    const size_t o_l = h_tri_label ? carve(sizeof(uint32_t) * (size_t)T) : 0;
+    if ((rc = lrc_grow(ctx, &ctx->mesh_dev, &ctx->mesh_dev_bytes, off))) return rc;
+    char* base = (char*)ctx->mesh_dev;
+    cudaStream_t st = ctx->s_compute;
+    if (V > 0) LRC_CUDA(ctx, cudaMemcpyAsync(base + o_v, h_verts, sizeof(float) * 3 * (size_t)V, cudaMemcpyHostToDevice, st));
+    if (T > 0) LRC_CUDA(ctx, cudaMemcpyAsync(base + o_t, h_tris, sizeof(int32_t) * 3 * (size_t)T, cudaMemcpyHostToDevice, st));
+    if (h_tri_label && T > 0) LRC_CUDA(ctx, cudaMemcpyAsync(base + o_l, h_tri_label, sizeof(uint32_t) * (size_t)T, cudaMemcpyHostToDevice, st));
+    return lrc_set_mesh(ctx, (const float*)(base + o_v), V, (const int32_t*)(base + o_t), T,
+                        h_tri_label ? (const uint32_t*)(base + o_l) : nullptr, st);
 }

@@ -86,6 +86,15 @@ class RaycastEngineGPU(RaycastEngineBase):
         t, pid = self.ctx.cast_rays(np.ascontiguousarray(rays, dtype=np.float32))
         return t.cpu().numpy(), pid.cpu().numpy().view(np.uint32)
 
+    def simulate_to_host(self, poses, intrinsics, mesh=None, noise: Optional[NoiseConfig] = None, host=None,
+                         chunk_poses: Optional[int] = None) -> dict:
+        """``simulate`` returning numpy arrays (points, incident, label, frame_offset) in pinned host memory; the
+        device-to-host copies are pipelined behind the traversal of later pose chunks (see Context.scan_to_host)."""
+        if mesh is not None:
+            self._prepare(mesh)
+        poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 4, 4)
+        return self.ctx.scan_to_host(poses, intrinsics, noise, host=host, chunk_poses=chunk_poses)
+
     def simulate(self, poses, intrinsics, mesh=None, noise: Optional[NoiseConfig] = None) -> ScanResult:
         """All frames of a trajectory at once.  ``poses``: (P,4,4) float64 (``Waypoint.to_pose_matrix``).
         Frame p of the result equals ``lidar_intersect_mesh(create_lidar(intrinsics, poses[p]), mesh)``."""

@@ -281,3 +281,18 @@ def test_unjittered_box_edges_and_corners(engine, lrc, orc):
     bt, bpid = orc.cast_rays_brute(_o3d_like(mesh), rays)
     assert np.array_equal(rpid, bpid) and np.array_equal(rt, bt)
     assert np.array_equal(pid, rpid) and np.array_equal(t, rt)
+
+
+def test_simulate_to_host_pipelined_equals_simulate(engine, lrc, c1):
+    """The host-output path (pose chunks, D2H overlapped with later chunks' kernels) returns the same bits."""
+    poses = lrc.poses_from_waypoints([lrc.Waypoint(2.0 + 0.5 * k, 3.0 + 0.2 * k, 1.0, 0.1 * k) for k in range(7)])
+    for intr, noise in ((lrc.Indoor8LineLidarIntrinsics(horizontal_res=720, max_range=6.0), None),
+                        (lrc.DualAxisLidarIntrinsics(point_rate=64000, scan_duration=0.1, max_range=5.0),
+                         lrc.NoiseConfig(0.001, 0.02, 0.0, seed=5, pose_index_base=3))):
+        ref = engine.simulate(poses, intr, c1["mesh"], noise=noise).numpy()
+        for chunk in (1, 2, 7, None):
+            got = engine.simulate_to_host(poses, intr, noise=noise, chunk_poses=chunk)
+            assert got["num_points"] == len(ref["points"]) > 1000
+            assert np.array_equal(got["frame_offset"], ref["frame_offset"])
+            assert np.array_equal(got["points"], ref["points"]) and np.array_equal(got["incident"], ref["incident"])
+            assert np.array_equal(got["label"], ref["label"])
