@@ -238,6 +238,9 @@ def run_reference(args):
 
 # ---- our arm -------------------------------------------------------------------------------------------
 def run_ours(args):
+    # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION/INFO: keep stdout to the one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
     import lrc_b200 as lrc
@@ -297,22 +300,26 @@ def run_ours(args):
     b_out = 12 + 8 + 4 + 4 + 4
     bytes_per_ray = nodes_per_ray * 64 + tris_per_ray * 48 + hit_frac * 4 + hit_frac * b_out
 
+    sharded, peer = None, None
+    if world > 1 and args.gather == "nccl":
+        from lrc_b200.distributed import OverlappedShardedScan
+        sharded = OverlappedShardedScan(ctx, poses, intr, noise, chunks=args.gather_chunks)
+    elif world > 1:
+        # fused compaction + all-gather: the compaction kernel stores every kept point into all ranks' buffers over
+        # NVLink peer memory, chunk by chunk, while the next chunk is traversed (lrc_set_gather)
+        from lrc_b200.distributed import PeerGather
+        peer = PeerGather(ctx, cap_per_rank=P * n_frame, frames_per_rank=P)
+        ctx.set_option("gather_chunks", args.gather_chunks)
+        peer.enable()
+
     def one_step():
-        ctx.scan_enqueue(poses_d, intr, noise, bufs)
+        if sharded is not None:
+            sharded.step()      # chunked scan; each chunk's xyz|label|offsets block is all-gathered (NCCL, async) behind the next chunk
+        else:
+            ctx.scan_enqueue(poses_d, intr, noise, bufs)
 
     def gather_step():
-        """Variable-length all-gather of the compacted clouds (counts first, then padded records)."""
-        m = bufs["off"][-1:].clone()
-        counts = [torch.zeros_like(m) for _ in range(world)]
-        dist.all_gather(counts, m)
-        mx = int(torch.stack(counts).max().item())
-        outs = {}
-        for key in ("xyz", "incident", "label"):
-            src = bufs[key][:mx].contiguous()
-            dst = torch.empty((world,) + tuple(src.shape), dtype=src.dtype, device=dev)
-            dist.all_gather_into_tensor(dst, src)
-            outs[key] = dst
-        return counts, outs
+        pass
 
     for _ in range(max(args.warmup, 3)):
         flush.fill_(1)
@@ -378,6 +385,10 @@ def run_ours(args):
                 "tris_per_ray": round(tris_per_ray, 2), "hit_fraction": round(hit_frac, 4),
                 "note": "algorithmic bytes; the 1M-tri BVH (112 MB) fits the 126 MB L2, so most of it is L2 traffic"}
 
+    if peer is not None:
+        peer.synchronize()
+        peer.disable()
+
     # ---- end to end through the reference-facing API with host buffers ----
     pinned_pose = torch.from_numpy(np.ascontiguousarray(poses.reshape(-1, 16))).pin_memory()
     pv, pf, pl = (torch.from_numpy(verts).pin_memory(), torch.from_numpy(tris).pin_memory(),
@@ -422,7 +433,10 @@ def run_ours(args):
             "config": {"workload": f"{args.workload}: {w['desc']}", "tris": int(len(tris)), "rays_per_frame": n_frame,
                        "poses_per_gpu": P, "poses_total": int(len(poses_all)), "parallelism": f"pose-sharded x{world}, replicated BVH",
                        "l2": "flushed between timed iterations (256 MiB fill)", "noise": bool(w["noise"]),
-                       "collective": "NCCL all-gather of compacted clouds inside the step" if world > 1 else "none"},
+                       "collective": ("none" if world == 1 else
+                                      f"fused in the compaction kernel: xyz|label|frame_offset stored to all {world} ranks over NVLink peer memory, "
+                                      f"{args.gather_chunks} chunks overlapped with traversal, inside the step" if args.gather == "p2p" else
+                                      f"NCCL all-gather of xyz|label|frame_offset blocks, {args.gather_chunks} chunks, overlapped with traversal, inside the step")},
             "frames_per_s": round(len(poses_all) / (ms_per_step * 1e-3), 1),
             "wall_ms_per_step_incl_flush": round(wall / args.steps * 1e3, 4),
             "bvh_build_ms": round(bvh_ms, 3), "bvh": {k: info[k] for k in ("num_nodes", "max_depth", "sah_cost", "bytes_nodes", "bytes_tris")},
@@ -432,6 +446,8 @@ def run_ours(args):
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
+    if peer is not None:
+        peer.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -447,6 +463,8 @@ def main():
     ap.add_argument("--tris", type=int, default=None, help="override the triangle count (debugging)")
     ap.add_argument("--poses", type=int, default=None, help="override poses per GPU (debugging)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N>1: how the clouds are exchanged")
+    ap.add_argument("--gather-chunks", type=int, default=4, help="N>1: pose chunks per rank for the overlapped all-gather")
     ap.add_argument("--e2e-chunk", type=int, default=None, help="poses per chunk of the pipelined e2e path")
     ap.add_argument("--variant", type=int, default=None, help="traversal kernel variant (lrc_set_option)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")

@@ -167,6 +167,32 @@ int lrc_scan_dual_axis_host(lrc_ctx* ctx, const double* h_poses, int64_t P, cons
 int lrc_set_mesh_host(lrc_ctx* ctx, const float* h_verts, int64_t V, const int32_t* h_tris, int64_t T,
                       const uint32_t* h_tri_label);
 
+/* ---- multi-GPU: fused compaction + all-gather over NVLink peer memory ------------------------ */
+/* The reference has no multi-process path; this is the exchange step of the pose-sharded run.
+ * A peer buffer is plain device memory whose CUDA IPC handle other ranks open; lrc_set_gather names up to 16
+ * target buffers (this GPU's own and the peers' mapped ones).  While targets are set, every scan's compaction kernel
+ * stores each kept point's xyz and label into EVERY target at point_base + position, and the frame offsets at
+ * frame_base + frame (+ the closing entry at frame_base + P), on top of the regular lrc_out.  The stores to peers
+ * travel over NVLink while the next pose chunk is being traversed.  Callers synchronise their stream and then
+ * barrier across ranks before reading. */
+#define LRC_MAX_GATHER_TARGETS 16
+typedef struct { unsigned char bytes[64]; } lrc_ipc_handle;
+typedef struct {
+    int32_t n_targets;
+    int32_t reserved;
+    float* xyz[LRC_MAX_GATHER_TARGETS];
+    uint32_t* label[LRC_MAX_GATHER_TARGETS];
+    int64_t* frame_offset[LRC_MAX_GATHER_TARGETS];
+    int64_t point_base;      /* first point slot of this rank's region inside every target */
+    int64_t frame_base;      /* first frame-offset slot of this rank's region */
+    int64_t capacity;        /* point slots available to this rank's region */
+} lrc_gather;
+int lrc_peer_buffer_create(lrc_ctx* ctx, int64_t bytes, void** d_ptr, lrc_ipc_handle* h_handle);
+int lrc_peer_buffer_open(lrc_ctx* ctx, const lrc_ipc_handle* h_handle, void** d_ptr);
+int lrc_peer_buffer_close(lrc_ctx* ctx, void* d_ptr);
+int lrc_peer_buffer_destroy(lrc_ctx* ctx, void* d_ptr);
+int lrc_set_gather(lrc_ctx* ctx, const lrc_gather* h_targets /* NULL or n_targets == 0: off */);
+
 /* ---- get_rays ------------------------------------------------------------------------------- */
 /* == IndoorLidar.get_rays (indoor_lidar.py:27-53): rays H*W x 6 float32, index j*W + i. */
 int lrc_gen_rays_single_axis(lrc_ctx* ctx, const double* poses, int64_t P, const lrc_single_axis* h_sensor,

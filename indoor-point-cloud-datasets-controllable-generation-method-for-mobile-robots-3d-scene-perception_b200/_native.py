@@ -45,6 +45,15 @@ class Out(C.Structure):                 # lrc_out
                 ("ray_idx", C.c_void_p), ("frame_offset", C.c_void_p), ("capacity", C.c_int64)]
 
 
+class IpcHandle(C.Structure):          # lrc_ipc_handle
+    _fields_ = [("bytes", C.c_ubyte * 64)]
+
+
+class Gather(C.Structure):             # lrc_gather
+    _fields_ = [("n_targets", C.c_int32), ("reserved", C.c_int32), ("xyz", C.c_void_p * 16), ("label", C.c_void_p * 16),
+                ("frame_offset", C.c_void_p * 16), ("point_base", C.c_int64), ("frame_base", C.c_int64), ("capacity", C.c_int64)]
+
+
 class Counters(C.Structure):            # lrc_counters_t
     _fields_ = [("rays", C.c_uint64), ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("hits", C.c_uint64)]
 
@@ -73,6 +82,11 @@ SYMBOLS = {
     "lrc_scan_single_axis_host": (_i32, [_vp, _vp, _i64, C.POINTER(SingleAxis), C.POINTER(Noise), C.POINTER(Out), _i64, C.POINTER(_i64)]),
     "lrc_scan_dual_axis_host": (_i32, [_vp, _vp, _i64, C.POINTER(DualAxis), C.POINTER(Noise), C.POINTER(Out), _i64, C.POINTER(_i64)]),
     "lrc_set_mesh_host": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp]),
+    "lrc_peer_buffer_create": (_i32, [_vp, _i64, C.POINTER(_vp), C.POINTER(IpcHandle)]),
+    "lrc_peer_buffer_open": (_i32, [_vp, C.POINTER(IpcHandle), C.POINTER(_vp)]),
+    "lrc_peer_buffer_close": (_i32, [_vp, _vp]),
+    "lrc_peer_buffer_destroy": (_i32, [_vp, _vp]),
+    "lrc_set_gather": (_i32, [_vp, C.POINTER(Gather)]),
     "lrc_gen_rays_single_axis": (_i32, [_vp, _vp, _i64, C.POINTER(SingleAxis), _vp, _vp]),
     "lrc_gen_rays_dual_axis": (_i32, [_vp, _vp, _i64, C.POINTER(DualAxis), C.POINTER(Noise), _vp, _vp, _vp]),
     "lrc_set_counting": (_i32, [_vp, _i32]),

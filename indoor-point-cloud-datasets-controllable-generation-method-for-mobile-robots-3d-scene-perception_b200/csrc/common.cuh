@@ -11,6 +11,7 @@
 
 #define LRC_STACK_DEPTH 64        // per-ray traversal stack entries (checked against the built tree)
 #define LRC_MAX_H 4096            // scan lines per single-axis sensor
+#define LRC_MAX_GATHER 16         // == lrc_gather's array length
 
 struct lrc_ctx {
     int device = 0;
@@ -47,6 +48,18 @@ struct lrc_ctx {
     size_t n_events = 0;
     void* mesh_dev = nullptr;          // device copies of host mesh arrays (lrc_set_mesh_host)
     size_t mesh_dev_bytes = 0;
+
+    // ---- pipelined compaction / multi-GPU gather ----
+    cudaStream_t s_aux = nullptr;      // compaction of chunk c runs here while chunk c+1 is traversed
+    cudaEvent_t pipe_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    struct {
+        int n = 0;
+        float* xyz[LRC_MAX_GATHER];
+        uint32_t* label[LRC_MAX_GATHER];
+        int64_t* frame_offset[LRC_MAX_GATHER];
+        int64_t point_base = 0, frame_base = 0, capacity = 0;
+    } gather;
+    int64_t opt_gather_chunks = 4;
 
     // ---- measurement ----
     unsigned long long* d_counters = nullptr;   // rays, nodes, tris, hits

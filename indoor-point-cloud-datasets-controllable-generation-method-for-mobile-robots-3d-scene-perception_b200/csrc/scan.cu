@@ -318,11 +318,25 @@ struct CompactParams {
     int64_t n;                 // rays in this launch
     int64_t ray0;              // global index of the first ray of this launch
     int64_t N;                 // rays per frame
+    int64_t total_rays;        // rays of the whole call (the owner of the last one writes the closing offset)
+    int64_t P;                 // frames of the whole call
     const uint32_t* labels;
     lrc_out out;
 };
 
-__global__ void __launch_bounds__(TRACE_THREADS) k_compact(CompactParams q)
+// Peer targets of the fused compaction + all-gather (lrc_set_gather): the same record is stored into every
+// target's buffer -- local HBM or another GPU's HBM mapped over NVLink (cudaIpcOpenMemHandle) -- at
+// point_base + position, so that after the kernel every GPU holds every rank's slice of the cloud.
+struct GatherTargets {
+    int n;
+    float* xyz[LRC_MAX_GATHER];
+    uint32_t* label[LRC_MAX_GATHER];
+    int64_t* frame_offset[LRC_MAX_GATHER];
+    int64_t point_base, frame_base, capacity;
+};
+
+template <bool GATHER>
+__global__ void __launch_bounds__(TRACE_THREADS) k_compact(CompactParams q, const __grid_constant__ GatherTargets gt)
 {
     __shared__ int s_warp[TRACE_THREADS / 32];
     const long long run0 = *q.run_in;
@@ -349,15 +363,31 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_compact(CompactParams q)
         const int64_t gidx = q.ray0 + i;
         const int64_t frame = gidx / q.N;
         const int64_t r = gidx - frame * q.N;
+        const bool closes = gidx == q.total_rays - 1;      // this thread owns the last ray of the call
         if (r == 0) q.out.frame_offset[frame] = pos;
+        uint32_t lab = 0u;
+        if (keep && (q.out.label || GATHER) && q.labels) lab = __ldg(q.labels + id);
         if (keep && pos < q.out.capacity) {
             q.out.xyz[3 * pos + 0] = h.x;
             q.out.xyz[3 * pos + 1] = h.y;
             q.out.xyz[3 * pos + 2] = h.z;
             if (q.out.incident_deg) q.out.incident_deg[pos] = inc;
             if (q.out.prim_id) q.out.prim_id[pos] = id;
-            if (q.out.label) q.out.label[pos] = __ldg(q.labels + id);
+            if (q.out.label) q.out.label[pos] = lab;
             if (q.out.ray_idx) q.out.ray_idx[pos] = (uint32_t)r;
+        }
+        if (GATHER) {
+            const long long gp = gt.point_base + pos;
+#pragma unroll 1
+            for (int k = 0; k < gt.n; ++k) {
+                if (keep && pos < gt.capacity) {
+                    float* x = gt.xyz[k] + 3 * gp;
+                    x[0] = h.x; x[1] = h.y; x[2] = h.z;
+                    gt.label[k][gp] = lab;
+                }
+                if (r == 0) gt.frame_offset[k][gt.frame_base + frame] = gp;
+                if (closes) gt.frame_offset[k][gt.frame_base + q.P] = gp + (keep ? 1 : 0);
+            }
         }
     }
 }
@@ -401,6 +431,8 @@ int check_out(lrc_ctx* ctx, const lrc_out* out, int64_t need)
 
 // Shared driver of all scan-type entry points: per chunk of whole frames, trace (+ block counts) -> scan of the
 // counts -> streaming compaction, with a running output offset carried in device memory (no host round trip).
+// With more than one chunk the compaction of chunk c (and, when gather targets are set, its NVLink stores) runs on
+// an auxiliary stream while chunk c+1 is traversed on the caller's stream; the scratch is double-buffered.
 template <int MODE>
 int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_center, double max_range, lrc_out* out,
              cudaStream_t stream)
@@ -409,56 +441,97 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
     int rc = check_out(ctx, out, total);
     if (rc) return rc;
     if ((rc = ensure_counters(ctx))) return rc;
+    const bool gather = ctx->gather.n > 0;
+    if (gather && ctx->gather.capacity < total) return lrc_fail(ctx, LRC_ERR_CAPACITY, "lrc_set_gather: capacity is smaller than the number of rays");
     if (total == 0) {
         LRC_CUDA(ctx, cudaMemsetAsync(out->frame_offset, 0, sizeof(int64_t) * (P + 1), stream));
         return LRC_OK;
     }
-    // chunk by whole frames so that scratch stays bounded (24 B per ray)
+    // chunk by whole frames: bounded scratch (24 B per ray per slot) and, with gather targets, overlap
     int64_t frames_per_chunk = ctx->opt_chunk_rays / N;
     if (frames_per_chunk < 1) frames_per_chunk = 1;
     if (MODE == MODE_RAYS) frames_per_chunk = P;   // a single explicit frame
+    if (gather && MODE != MODE_RAYS && ctx->opt_gather_chunks > 1) {
+        const int64_t want = (P + ctx->opt_gather_chunks - 1) / ctx->opt_gather_chunks;
+        if (want >= 1 && want < frames_per_chunk) frames_per_chunk = want;
+    }
     const int64_t n_chunks = (P + frames_per_chunk - 1) / frames_per_chunk;
+    const bool piped = n_chunks > 1;
+    const int n_slots = piped ? 2 : 1;
     const int64_t chunk_rays = frames_per_chunk * N;
     const int64_t max_blocks = (chunk_rays + TRACE_THREADS - 1) / TRACE_THREADS;
     const bool want_inc = out->incident_deg != nullptr && max_range >= 0.0;
     const size_t hp_bytes = align_up(sizeof(float4) * (size_t)chunk_rays, 256);
     const size_t inc_bytes = want_inc ? align_up(sizeof(double) * (size_t)chunk_rays, 256) : 0;
-    if ((rc = lrc_grow(ctx, &ctx->scratch, &ctx->scratch_bytes, hp_bytes + inc_bytes))) return rc;
+    const size_t slot_bytes = hp_bytes + inc_bytes;
+    if ((rc = lrc_grow(ctx, &ctx->scratch, &ctx->scratch_bytes, slot_bytes * n_slots))) return rc;
     // the scratch is shared by every scan of this context: order this call after the previous one, whatever its stream
     if (!ctx->scratch_event) LRC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->scratch_event, cudaEventDisableTiming));
     else LRC_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->scratch_event, 0));
     const size_t cnt_bytes = align_up(sizeof(unsigned) * (size_t)max_blocks, 256);
-    const size_t need2 = 2 * cnt_bytes + sizeof(long long) * (size_t)(n_chunks + 1);
+    const size_t need2 = 2 * cnt_bytes * n_slots + sizeof(long long) * (size_t)(n_chunks + 1);
     if ((rc = lrc_grow(ctx, &ctx->scratch2, &ctx->scratch2_bytes, need2))) return rc;
     char* b2 = (char*)ctx->scratch2;
-    unsigned* counts = (unsigned*)b2;
-    unsigned* base = (unsigned*)(b2 + cnt_bytes);
-    long long* run = (long long*)(b2 + 2 * cnt_bytes);
+    long long* run = (long long*)(b2 + 2 * cnt_bytes * n_slots);
     LRC_CUDA(ctx, cudaMemsetAsync(run, 0, sizeof(long long), stream));
-    float4* hp = (float4*)ctx->scratch;
-    double* inc = want_inc ? (double*)((char*)ctx->scratch + hp_bytes) : nullptr;
+    cudaStream_t aux = stream;
+    if (piped) {
+        if (!ctx->s_aux) {
+            int lo = 0, hi = 0;
+            LRC_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            LRC_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->s_aux, cudaStreamNonBlocking, hi));   // compaction blocks are short: let them in first
+            for (int k = 0; k < 4; ++k) LRC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_ev[k], cudaEventDisableTiming));
+        }
+        aux = ctx->s_aux;
+        LRC_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[3], stream));      // aux must see the memset of run[0] and the tables
+        LRC_CUDA(ctx, cudaStreamWaitEvent(aux, ctx->pipe_ev[3], 0));
+    }
     FrameMath fm;
     fm.max_range = max_range;
     fm.cx = h_center ? h_center[0] : 0.0; fm.cy = h_center ? h_center[1] : 0.0; fm.cz = h_center ? h_center[2] : 0.0;
+    GatherTargets gt;
+    memset(&gt, 0, sizeof gt);
+    if (gather) {
+        gt.n = ctx->gather.n;
+        for (int k = 0; k < gt.n; ++k) { gt.xyz[k] = ctx->gather.xyz[k]; gt.label[k] = ctx->gather.label[k]; gt.frame_offset[k] = ctx->gather.frame_offset[k]; }
+        gt.point_base = ctx->gather.point_base; gt.frame_base = ctx->gather.frame_base; gt.capacity = ctx->gather.capacity;
+    }
     for (int64_t c = 0; c < n_chunks; ++c) {
+        const int slot = piped ? (int)(c & 1) : 0;
         const int64_t f0 = c * frames_per_chunk;
         const int64_t nf = (f0 + frames_per_chunk <= P) ? frames_per_chunk : P - f0;
         const int64_t n = nf * N;
         const int64_t nb = (n + TRACE_THREADS - 1) / TRACE_THREADS;
+        float4* hp = (float4*)((char*)ctx->scratch + slot_bytes * slot);
+        double* inc = want_inc ? (double*)((char*)ctx->scratch + slot_bytes * slot + hp_bytes) : nullptr;
+        unsigned* counts = (unsigned*)(b2 + 2 * cnt_bytes * slot);
+        unsigned* base = (unsigned*)(b2 + 2 * cnt_bytes * slot + cnt_bytes);
         g.pose0 = f0;
+        if (piped && c >= 2) LRC_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->pipe_ev[slot], 0));   // slot free again?
         if ((rc = launch_trace<MODE, false>(ctx, g, fm, n, hp, inc, counts, nullptr, nullptr, stream))) return rc;
+        if (piped) {
+            LRC_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[2], stream));
+            LRC_CUDA(ctx, cudaStreamWaitEvent(aux, ctx->pipe_ev[2], 0));
+        }
         const bool last = (c == n_chunks - 1);
-        k_scan_counts<<<1, 1024, 0, stream>>>(counts, base, nb, run + c, run + c + 1, last ? out->frame_offset + P : nullptr);
+        k_scan_counts<<<1, 1024, 0, aux>>>(counts, base, nb, run + c, run + c + 1, last ? out->frame_offset + P : nullptr);
         LRC_CHECK_LAUNCH(ctx, "k_scan_counts");
         CompactParams q;
         q.hp = hp; q.inc = inc; q.base = base; q.run_in = run + c;
-        q.n = n; q.ray0 = f0 * N; q.N = N;
-        q.labels = ctx->labels;
+        q.n = n; q.ray0 = f0 * N; q.N = N; q.total_rays = total; q.P = P;
+        q.labels = ctx->T > 0 ? ctx->labels : nullptr;
         q.out = *out;
         if (!want_inc) q.out.incident_deg = nullptr;
         if (ctx->T == 0) q.out.label = nullptr;
-        k_compact<<<(unsigned)nb, TRACE_THREADS, 0, stream>>>(q);
+        if (gather) k_compact<true><<<(unsigned)nb, TRACE_THREADS, 0, aux>>>(q, gt);
+        else k_compact<false><<<(unsigned)nb, TRACE_THREADS, 0, aux>>>(q, gt);
         LRC_CHECK_LAUNCH(ctx, "k_compact");
+        if (piped) LRC_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[slot], aux));
+    }
+    if (piped) {   // the caller's stream owns the result: join the auxiliary stream back
+        const int last_slot = (int)((n_chunks - 1) & 1);
+        LRC_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->pipe_ev[last_slot], 0));
+        if (n_chunks >= 2) LRC_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->pipe_ev[last_slot ^ 1], 0));
     }
     LRC_CUDA(ctx, cudaEventRecord(ctx->scratch_event, stream));
     if (out->incident_deg && !want_inc)   // rays_intersect_mesh flavour: no angles are defined; keep the buffer deterministic
@@ -556,6 +629,7 @@ extern "C" void lrc_destroy(lrc_ctx* ctx)
     cudaFree(ctx->host_dev); cudaFree(ctx->mesh_dev);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->scratch_event) cudaEventDestroy(ctx->scratch_event);
+    if (ctx->s_aux) { cudaStreamDestroy(ctx->s_aux); for (int k = 0; k < 4; ++k) cudaEventDestroy(ctx->pipe_ev[k]); }
     for (size_t i = 0; i < ctx->n_events; ++i) cudaEventDestroy(ctx->events[i]);
     free(ctx->events);
     if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
@@ -593,6 +667,7 @@ extern "C" int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value)
 {
     if (!ctx || !key) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_option: NULL argument");
     if (!strcmp(key, "chunk_rays")) { if (value < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "chunk_rays must be >= 1"); ctx->opt_chunk_rays = value; return LRC_OK; }
+    if (!strcmp(key, "gather_chunks")) { if (value < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "gather_chunks must be >= 1"); ctx->opt_gather_chunks = value; return LRC_OK; }
     if (!strcmp(key, "variant")) {
         if (value < 0 || value > 1) return lrc_fail(ctx, LRC_ERR_INVALID, "variant must be 0 or 1");
         ctx->opt_variant = value;
@@ -871,4 +946,67 @@ extern "C" int lrc_set_mesh_host(lrc_ctx* ctx, const float* h_verts, int64_t V, 
     if (h_tri_label && T > 0) LRC_CUDA(ctx, cudaMemcpyAsync(base + o_l, h_tri_label, sizeof(uint32_t) * (size_t)T, cudaMemcpyHostToDevice, st));
     return lrc_set_mesh(ctx, (const float*)(base + o_v), V, (const int32_t*)(base + o_t), T,
                         h_tri_label ? (const uint32_t*)(base + o_l) : nullptr, st);
+}
+
+// ======================================================================================================
+// Multi-GPU exchange over NVLink peer memory: buffers that other processes map with CUDA IPC, and the gather
+// targets the compaction kernel stores into.
+extern "C" int lrc_peer_buffer_create(lrc_ctx* ctx, int64_t bytes, void** d_ptr, lrc_ipc_handle* h_handle)
+{
+    if (!ctx || !d_ptr || !h_handle || bytes <= 0) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_peer_buffer_create: bad arguments");
+    LRC_CUDA(ctx, cudaSetDevice(ctx->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(lrc_ipc_handle), "handle size");
+    void* p = nullptr;
+    LRC_CUDA(ctx, cudaMalloc(&p, (size_t)bytes));
+    LRC_CUDA(ctx, cudaMemset(p, 0, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return lrc_fail(ctx, LRC_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+    memset(h_handle, 0, sizeof *h_handle);
+    memcpy(h_handle, &h, sizeof h);
+    *d_ptr = p;
+    return LRC_OK;
+}
+
+extern "C" int lrc_peer_buffer_open(lrc_ctx* ctx, const lrc_ipc_handle* h_handle, void** d_ptr)
+{
+    if (!ctx || !d_ptr || !h_handle) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_peer_buffer_open: bad arguments");
+    LRC_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, h_handle, sizeof h);
+    LRC_CUDA(ctx, cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return LRC_OK;
+}
+
+extern "C" int lrc_peer_buffer_close(lrc_ctx* ctx, void* d_ptr)
+{
+    if (!ctx) return lrc_fail(nullptr, LRC_ERR_INVALID, "lrc_peer_buffer_close: ctx is NULL");
+    LRC_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (d_ptr) LRC_CUDA(ctx, cudaIpcCloseMemHandle(d_ptr));
+    return LRC_OK;
+}
+
+extern "C" int lrc_peer_buffer_destroy(lrc_ctx* ctx, void* d_ptr)
+{
+    if (!ctx) return lrc_fail(nullptr, LRC_ERR_INVALID, "lrc_peer_buffer_destroy: ctx is NULL");
+    LRC_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (d_ptr) LRC_CUDA(ctx, cudaFree(d_ptr));
+    return LRC_OK;
+}
+
+extern "C" int lrc_set_gather(lrc_ctx* ctx, const lrc_gather* h_targets)
+{
+    if (!ctx) return lrc_fail(nullptr, LRC_ERR_INVALID, "lrc_set_gather: ctx is NULL");
+    if (!h_targets || h_targets->n_targets == 0) { memset(&ctx->gather, 0, sizeof ctx->gather); return LRC_OK; }
+    if (h_targets->n_targets < 0 || h_targets->n_targets > LRC_MAX_GATHER) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_gather: n_targets out of range");
+    for (int k = 0; k < h_targets->n_targets; ++k)
+        if (!h_targets->xyz[k] || !h_targets->label[k] || !h_targets->frame_offset[k])
+            return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_gather: every target needs xyz, label and frame_offset");
+    if (h_targets->point_base < 0 || h_targets->frame_base < 0 || h_targets->capacity < 0) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_gather: negative base");
+    ctx->gather.n = h_targets->n_targets;
+    for (int k = 0; k < h_targets->n_targets; ++k) {
+        ctx->gather.xyz[k] = h_targets->xyz[k]; ctx->gather.label[k] = h_targets->label[k]; ctx->gather.frame_offset[k] = h_targets->frame_offset[k];
+    }
+    ctx->gather.point_base = h_targets->point_base; ctx->gather.frame_base = h_targets->frame_base; ctx->gather.capacity = h_targets->capacity;
+    return LRC_OK;
 }

@@ -106,3 +106,214 @@ def simulate_sharded(engine, poses_all, intrinsics, mesh=None, noise=None, group
     local = {"points": res.points, "incident": res.incident, "prim_id": res.prim_id, "label": res.label, "ray_idx": res.ray_idx}
     counts = (res.frame_offset[1:] - res.frame_offset[:-1]).contiguous()
     return allgather_clouds(local, counts, len(poses_all), group=group)
+
+
+class OverlappedShardedScan:
+    """Steady-state multi-GPU trajectory scan with the cloud exchange hidden behind the traversal.
+
+    This rank's pose slice is cut into ``chunks`` pieces.  Every chunk writes its compacted ``xyz | label |
+    frame_offset`` into ONE contiguous device block of fixed capacity; as soon as a chunk's kernels are done an
+    asynchronous all-gather of that block runs on the communicator's stream while the next chunk is traversed.  No
+    host synchronisation happens inside ``step()`` (fixed-capacity blocks need no counts on the host; the gathered
+    per-frame offsets say which part of every block is valid).
+
+    Gathered layout, per chunk c: ``gathered[c]`` is a (world, block_bytes) uint8 tensor; ``views(c, r)`` returns the
+    (xyz, label, frame_offset) views of rank r's chunk c.  Incident angles stay local: they are a pure function of a
+    point and its frame pose (reference raycast_engine_cpu.py:100-107) and moving them would add 50 % link traffic.
+    """
+
+    def __init__(self, ctx, poses_local, intrinsics, noise=None, chunks: int = 4, group=None):
+        from . import core
+        self.ctx, self.intr, self.group = ctx, intrinsics, group
+        self.rank, self.world = world_info(group)
+        dev = ctx.device
+        self.n_frame = core.rays_per_frame(intrinsics)
+        poses_local = np.ascontiguousarray(poses_local, dtype=np.float64).reshape(-1, 16)
+        self.P = len(poses_local)
+        self.poses_d = torch.from_numpy(poses_local).to(dev)
+        chunks = max(1, min(int(chunks), self.P)) if self.P > 0 else 1
+        bounds = [(self.P * c) // chunks for c in range(chunks + 1)]
+        self.ranges = [(bounds[c], bounds[c + 1]) for c in range(chunks) if bounds[c + 1] > bounds[c]]
+        self.noise = noise
+        self.comm = torch.cuda.Stream(dev)
+        self.blocks, self.layout, self.bufs, self.gathered = [], [], [], []
+        for (a, b) in self.ranges:
+            nf, cap = b - a, (b - a) * self.n_frame
+            o_lab = cap * 12
+            o_off = (o_lab + cap * 4 + 255) // 256 * 256
+            nbytes = (o_off + (nf + 1) * 8 + 255) // 256 * 256
+            blk = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+            xyz = blk[: cap * 12].view(torch.float32).view(cap, 3)
+            lab = blk[o_lab: o_lab + cap * 4].view(torch.int32)
+            off = blk[o_off: o_off + (nf + 1) * 8].view(torch.int64)
+            self.blocks.append(blk)
+            self.layout.append((cap, nf, o_lab, o_off))
+            self.bufs.append({"xyz": xyz, "incident": torch.empty(cap, dtype=torch.float64, device=dev), "prim": None,
+                              "label": lab, "ray": None, "off": off})
+            self.gathered.append(torch.empty((self.world, nbytes), dtype=torch.uint8, device=dev) if self.world > 1 else blk.view(1, -1))
+
+    def step(self):
+        """Enqueue one whole trajectory pass (+ exchange).  Returns after enqueueing; the caller's stream is made to
+        wait for the exchange, so an event recorded afterwards covers everything."""
+        from .core import NoiseConfig
+        main = torch.cuda.current_stream(self.ctx.device)
+        works = []
+        for c, (a, b) in enumerate(self.ranges):
+            nz = None
+            if self.noise is not None:
+                nz = NoiseConfig(self.noise.angle_noise_std, self.noise.dropout_probability, self.noise.range_noise_std,
+                                 self.noise.seed, self.noise.pose_index_base + a)
+            self.ctx.scan_enqueue(self.poses_d[a:b], self.intr, nz, self.bufs[c])
+            if self.world > 1:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(self.comm):
+                    self.comm.wait_event(ev)
+                    works.append(dist.all_gather_into_tensor(self.gathered[c].view(-1), self.blocks[c], group=self.group, async_op=True))
+        for w in works:
+            w.wait()          # the caller's current stream waits for the collective, the host does not
+        return works
+
+    def views(self, c: int, r: int):
+        cap, nf, o_lab, o_off = self.layout[c]
+        g = self.gathered[c][r]
+        return (g[: cap * 12].view(torch.float32).view(cap, 3), g[o_lab: o_lab + cap * 4].view(torch.int32),
+                g[o_off: o_off + (nf + 1) * 8].view(torch.int64))
+
+    def assemble_numpy(self) -> Dict[str, np.ndarray]:
+        """Dense, pose-ordered cloud of ALL ranks (testing / export; synchronises).  Requires every rank to have used
+        the same chunking, which holds when shards have equal sizes."""
+        torch.cuda.synchronize(self.ctx.device)
+        pts, labs, counts = [], [], []
+        for r in range(self.world):
+            for c in range(len(self.ranges)):
+                xyz, lab, off = self.views(c, r)
+                o = off.cpu().numpy()
+                m = int(o[-1])
+                pts.append(xyz[:m].cpu().numpy()); labs.append(lab[:m].cpu().numpy().view(np.uint32))
+                counts.append(np.diff(o))
+        cnt = np.concatenate(counts) if counts else np.zeros(0, np.int64)
+        return {"points": np.concatenate(pts), "label": np.concatenate(labs),
+                "frame_offset": np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)}
+
+
+class _RawCudaBuffer:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can view it without a copy."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class PeerGather:
+    """Fused compaction + all-gather over NVLink peer memory (``lrc_set_gather``).
+
+    Every rank owns one buffer ``[xyz: world*cap x 3 f32 | label: world*cap u32 | frame_offset: world*(Pmax+1) i64]``
+    allocated by the engine and mapped by all other ranks through CUDA IPC.  While enabled, the compaction kernel of
+    every scan stores rank r's compacted points into region r of ALL buffers (its own and the peers'), chunk by chunk,
+    while the next pose chunk is traversed -- there is no separate collective.  After ``synchronize()`` (stream sync
+    + barrier) each rank holds the whole cloud: frame f of rank r is
+    ``xyz[r*cap + off[r, f] - r*cap ...]`` -- see ``views`` / ``assemble_numpy``.
+    """
+
+    def __init__(self, ctx, cap_per_rank: int, frames_per_rank: int, group=None):
+        import ctypes as C
+        from . import _native as nat
+        self.ctx, self.group = ctx, group
+        self.rank, self.world = world_info(group)
+        if self.world > nat.Gather.xyz.size // C.sizeof(C.c_void_p):
+            raise ValueError("PeerGather supports at most 16 ranks")
+        self.cap, self.pmax = int(cap_per_rank), int(frames_per_rank)
+        w = self.world
+        self.o_lab = (w * self.cap * 12 + 255) // 256 * 256
+        self.o_off = (self.o_lab + w * self.cap * 4 + 255) // 256 * 256
+        self.nbytes = (self.o_off + w * (self.pmax + 1) * 8 + 255) // 256 * 256
+        lib = ctx._lib
+        ptr, handle = C.c_void_p(), nat.IpcHandle()
+        with torch.cuda.device(ctx.device):
+            nat.check(ctx._h, lib.lrc_peer_buffer_create(ctx._h, self.nbytes, C.byref(ptr), C.byref(handle)))
+        self.local_ptr = ptr.value
+        handles = [None] * w
+        if w > 1:
+            dist.all_gather_object(handles, bytes(handle.bytes), group=group)
+        else:
+            handles[0] = bytes(handle.bytes)
+        self.ptrs, self._opened = [], []
+        for r in range(w):
+            if r == self.rank:
+                self.ptrs.append(self.local_ptr)
+                continue
+            h = nat.IpcHandle()
+            C.memmove(C.byref(h), handles[r], 64)
+            p = C.c_void_p()
+            with torch.cuda.device(ctx.device):
+                nat.check(ctx._h, lib.lrc_peer_buffer_open(ctx._h, C.byref(h), C.byref(p)))
+            self.ptrs.append(p.value)
+            self._opened.append(p.value)
+        g = nat.Gather()
+        g.n_targets = w
+        for r in range(w):
+            g.xyz[r] = self.ptrs[r]
+            g.label[r] = self.ptrs[r] + self.o_lab
+            g.frame_offset[r] = self.ptrs[r] + self.o_off
+        g.point_base = self.rank * self.cap
+        g.frame_base = self.rank * (self.pmax + 1)
+        g.capacity = self.cap
+        self._g = g
+        self.buffer = torch.as_tensor(_RawCudaBuffer(self.local_ptr, self.nbytes), device=ctx.device)
+        if w > 1:
+            dist.barrier(group=group)
+
+    def enable(self):
+        import ctypes as C
+        from . import _native as nat
+        nat.check(self.ctx._h, self.ctx._lib.lrc_set_gather(self.ctx._h, C.byref(self._g)))
+
+    def disable(self):
+        from . import _native as nat
+        nat.check(self.ctx._h, self.ctx._lib.lrc_set_gather(self.ctx._h, None))
+
+    def synchronize(self):
+        """Make every rank's stores visible here: local stream sync, then a barrier across ranks."""
+        torch.cuda.synchronize(self.ctx.device)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def views(self):
+        w = self.world
+        xyz = self.buffer[: w * self.cap * 12].view(torch.float32).view(w, self.cap, 3)
+        lab = self.buffer[self.o_lab: self.o_lab + w * self.cap * 4].view(torch.int32).view(w, self.cap)
+        off = self.buffer[self.o_off: self.o_off + w * (self.pmax + 1) * 8].view(torch.int64).view(w, self.pmax + 1)
+        return xyz, lab, off
+
+    def assemble_numpy(self, frames_per_rank: Optional[List[int]] = None) -> Dict[str, np.ndarray]:
+        """Dense, pose-ordered cloud of all ranks (testing / export)."""
+        xyz, lab, off = self.views()
+        pts, labs, counts = [], [], []
+        for r in range(self.world):
+            nf = self.pmax if frames_per_rank is None else frames_per_rank[r]
+            o = off[r, : nf + 1].cpu().numpy() - r * self.cap
+            m = int(o[-1])
+            pts.append(xyz[r, :m].cpu().numpy()); labs.append(lab[r, :m].cpu().numpy().view(np.uint32))
+            counts.append(np.diff(o))
+        cnt = np.concatenate(counts)
+        return {"points": np.concatenate(pts), "label": np.concatenate(labs),
+                "frame_offset": np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)}
+
+    def close(self):
+        lib = self.ctx._lib
+        try:
+            self.disable()
+            with torch.cuda.device(self.ctx.device):
+                torch.cuda.synchronize()
+                if self.world > 1:
+                    dist.barrier(group=self.group)
+                for p in self._opened:
+                    lib.lrc_peer_buffer_close(self.ctx._h, p)
+                self._opened = []
+                if self.world > 1:
+                    dist.barrier(group=self.group)
+                if self.local_ptr:
+                    lib.lrc_peer_buffer_destroy(self.ctx._h, self.local_ptr)
+                    self.local_ptr = None
+        except Exception:
+            pass

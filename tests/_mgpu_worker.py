@@ -27,6 +27,38 @@ def main():
         for k in ref:
             assert np.array_equal(got[k], ref[k]), (dist.get_rank(), type(intr).__name__, k)
         assert got["frame_offset"][-1] > 10000
+    # steady-state overlapped path (what bench.py times for N > 1): xyz|label blocks gathered chunk by chunk
+    from lrc_b200.distributed import OverlappedShardedScan
+    world, rank = dist.get_world_size(), dist.get_rank()
+    poses12 = lrc.poses_from_waypoints([lrc.Waypoint(1.5 + 0.5 * k, 3.2 + 0.1 * k, 1.0, 0.05 * k) for k in range(6 * world)])
+    intr = lrc.DualAxisLidarIntrinsics.create_blk2go_dual_axis()
+    noise = lrc.NoiseConfig.from_intrinsics(intr, seed=5, pose_index_base=0)
+    sl = lrc.shard_range(len(poses12), rank, world)
+    local_noise = lrc.NoiseConfig(noise.angle_noise_std, noise.dropout_probability, 0.0, noise.seed, sl.start)
+    run = OverlappedShardedScan(engine.ctx, poses12[sl.start:sl.stop], intr, local_noise, chunks=3)
+    for _ in range(2):
+        run.step()
+    got = run.assemble_numpy()
+    ref = engine.simulate(poses12, intr, mesh, noise=noise).numpy()
+    assert np.array_equal(got["frame_offset"], ref["frame_offset"])
+    assert np.array_equal(got["points"], ref["points"]) and np.array_equal(got["label"], ref["label"])
+    # fused compaction + all-gather over NVLink peer memory (lrc_set_gather): no collective at all
+    from lrc_b200.distributed import PeerGather
+    pg = PeerGather(engine.ctx, cap_per_rank=6 * 64000, frames_per_rank=6)
+    pg.enable()
+    engine.ctx.set_option("gather_chunks", 3)
+    try:
+        for _ in range(2):
+            local = engine.simulate(poses12[sl.start:sl.stop], intr, noise=local_noise).numpy()
+        pg.synchronize()
+        got = pg.assemble_numpy()
+    finally:
+        pg.disable()
+    assert np.array_equal(got["frame_offset"], ref["frame_offset"])
+    assert np.array_equal(got["points"], ref["points"]) and np.array_equal(got["label"], ref["label"])
+    a, b = ref["frame_offset"][sl.start], ref["frame_offset"][sl.stop]
+    assert np.array_equal(local["points"], ref["points"][a:b]) and np.array_equal(local["incident"], ref["incident"][a:b])
+    pg.close()
     dist.barrier()
     if dist.get_rank() == 0:
         print("MGPU_OK world=%d" % dist.get_world_size())

@@ -296,3 +296,28 @@ def test_simulate_to_host_pipelined_equals_simulate(engine, lrc, c1):
             assert np.array_equal(got["frame_offset"], ref["frame_offset"])
             assert np.array_equal(got["points"], ref["points"]) and np.array_equal(got["incident"], ref["incident"])
             assert np.array_equal(got["label"], ref["label"])
+
+
+def test_gather_targets_and_pipelined_compaction_single_gpu(engine, lrc, c1):
+    """lrc_set_gather with this GPU's own buffer as the only target: the fused store path and the two-stream
+    chunk pipeline (compaction of chunk c behind the traversal of chunk c+1) must not change a bit."""
+    from lrc_b200.distributed import PeerGather
+    poses = lrc.poses_from_waypoints([lrc.Waypoint(2.0 + 0.5 * k, 3.0 + 0.2 * k, 1.0, 0.1 * k) for k in range(7)])
+    intr = lrc.Indoor8LineLidarIntrinsics(horizontal_res=720, max_range=6.0)
+    ref = engine.simulate(poses, intr, c1["mesh"]).numpy()
+    pg = PeerGather(engine.ctx, cap_per_rank=7 * 8 * 720, frames_per_rank=7)
+    try:
+        for chunks in (1, 2, 3, 7):
+            engine.ctx.set_option("gather_chunks", chunks)
+            pg.enable()
+            got_local = engine.simulate(poses, intr).numpy()
+            pg.synchronize()
+            got = pg.assemble_numpy()
+            pg.disable()
+            for k in ref:
+                assert np.array_equal(got_local[k], ref[k]), (chunks, k)
+            assert np.array_equal(got["frame_offset"], ref["frame_offset"])
+            assert np.array_equal(got["points"], ref["points"]) and np.array_equal(got["label"], ref["label"])
+    finally:
+        engine.ctx.set_option("gather_chunks", 4)
+        pg.close()
