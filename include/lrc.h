@@ -202,6 +202,28 @@ int lrc_gen_rays_single_axis(lrc_ctx* ctx, const double* poses, int64_t P, const
 int lrc_gen_rays_dual_axis(lrc_ctx* ctx, const double* poses, int64_t P, const lrc_dual_axis* h_sensor,
                            const lrc_noise* h_noise, float* rays, uint8_t* keep, void* stream);
 
+/* ---- after the cast: per-frame statistics and the labelled-PLY wire format ------------ */
+/* == the ScanQuality sums of the frame loop (s3dis_simulator.py:276-284): per frame num_points, np.mean / np.std
+ *    (population) of the float64 incident angles, and np.mean / np.std of np.linalg.norm(points, axis=1) -- float32
+ *    norms taken from the WORLD ORIGIN, as the reference does.  Sums are carried in float64 in a fixed order
+ *    (deterministic); coverage_ratio and scan_density are num_points divided by host constants.  incident_deg may be
+ *    NULL (angle fields are then 0).  out: P records, device. */
+typedef struct {
+    int64_t num_points;
+    double incident_mean, incident_std;
+    double range_mean, range_std;
+} lrc_frame_stats;
+int lrc_frame_statistics(lrc_ctx* ctx, const float* xyz, const double* incident_deg, const int64_t* frame_offset,
+                         int64_t P, lrc_frame_stats* out, void* stream);
+/* == the vertex records S3DISSimScene._save_labeled_ply writes with struct.pack per point
+ *    (containers/s3dis_sim_scene.py:634-641): M x 19 bytes, little endian, '<fff BBB HH' =
+ *    x y z | red green blue | sem ins.  label = sem | ins << 16 (NULL: both 0, the reference's default labels,
+ *    s3dis_sim_scene.py:584-594).  Colour: tri_rgb[prim_id[i]] (red | green << 8 | blue << 16) when both are given,
+ *    else default_rgb (0x7F7F7F is the reference's default grey, (0.5 * 255).astype(uint8)).  out: 19 * M bytes,
+ *    16-byte aligned, device.  The caller prepends the text header (:621-632) and writes the bytes. */
+int lrc_pack_ply_records(lrc_ctx* ctx, const float* xyz, const uint32_t* label, const uint32_t* prim_id,
+                         const uint32_t* tri_rgb, uint32_t default_rgb, int64_t M, uint8_t* out, void* stream);
+
 /* ---- measurement ---------------------------------------------------------------------------- */
 /* Work counters, accumulated by cast/scan calls while counting is enabled (a separate, slower
  * instantiation of the traversal kernel).  lrc_counters synchronises `stream` first. */
@@ -209,7 +231,13 @@ int lrc_set_counting(lrc_ctx* ctx, int enabled);
 int lrc_counters(lrc_ctx* ctx, lrc_counters_t* h_out, int reset, void* stream);
 /* Number of kernel launches issued by this context since creation (for bench.py's gpu_launches). */
 int64_t lrc_launch_count(const lrc_ctx* ctx);
-/* Traversal kernel variant / tuning knob: 0 = default.  Unknown keys -> LRC_ERR_INVALID. */
+/* Device time of the traversal kernel (k_trace) and of the ordered compaction (k_scan_counts + k_compact) of the LAST
+ * scan call, from CUDA events recorded on the streams those kernels were launched on; summed over the call's pose
+ * chunks (*h_launches = number of chunks = k_trace launches).  Requires lrc_set_option(ctx, "kernel_timing", 1)
+ * before the scan; synchronises on the recorded events.  This is what bench.py's roofline divides by. */
+int lrc_kernel_times(lrc_ctx* ctx, double* h_trace_ms, double* h_compact_ms, int32_t* h_launches);
+/* Tuning knobs: "variant" (traversal loop shape), "chunk_rays", "gather_chunks", "kernel_timing".
+ * Unknown keys -> LRC_ERR_INVALID. */
 int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value);
 
 #ifdef __cplusplus

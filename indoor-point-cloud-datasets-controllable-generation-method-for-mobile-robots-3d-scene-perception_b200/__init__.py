@@ -11,18 +11,22 @@ The directory name contains hyphens, so import it through the alias package::
 Sub-packages keep the reference's module names: ``lidar`` (sensor model) and ``raycast_engine`` (engine).
 Importing the package needs neither a GPU nor the built library; creating an engine needs both.
 """
-from . import lidar, raycast_engine, synthetic, trajectory
+from . import lidar, post, raycast_engine, synthetic, trajectory
 from .core import (Context, NoiseConfig, ScanResult, TriangleMesh, get_context, mesh_arrays, pack_labels,
                    rays_per_frame, unpack_labels)
 from .lidar import (DualAxisLidar, DualAxisLidarIntrinsics, Indoor8LineLidarIntrinsics, IndoorLidar, LidarIntrinsics,
                     create_lidar, get_lidar_type)
 from .raycast_engine import RaycastEngineBase, RaycastEngineGPU
+from .post import (ScanQuality, SimulationStats, frame_statistics, read_labeled_ply, scan_quality, simulation_stats,
+                   write_labeled_ply)
 from .trajectory import Waypoint, poses_from_waypoints, shard_range
 
 __version__ = "0.1.0"
 
 __all__ = [
-    "lidar", "raycast_engine", "synthetic", "trajectory",
+    "lidar", "post", "raycast_engine", "synthetic", "trajectory",
+    "ScanQuality", "SimulationStats", "frame_statistics", "scan_quality", "simulation_stats", "write_labeled_ply",
+    "read_labeled_ply",
     "Context", "NoiseConfig", "ScanResult", "TriangleMesh", "get_context", "mesh_arrays", "pack_labels",
     "unpack_labels", "rays_per_frame",
     "LidarIntrinsics", "Indoor8LineLidarIntrinsics", "DualAxisLidarIntrinsics", "IndoorLidar", "DualAxisLidar",

@@ -58,6 +58,11 @@ class Counters(C.Structure):            # lrc_counters_t
     _fields_ = [("rays", C.c_uint64), ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("hits", C.c_uint64)]
 
 
+class FrameStats(C.Structure):          # lrc_frame_stats
+    _fields_ = [("num_points", C.c_int64), ("incident_mean", C.c_double), ("incident_std", C.c_double),
+                ("range_mean", C.c_double), ("range_std", C.c_double)]
+
+
 class BvhInfo(C.Structure):             # lrc_bvh_info
     _fields_ = [("num_tris", C.c_int64), ("num_nodes", C.c_int64), ("max_depth", C.c_int32), ("reserved", C.c_int32),
                 ("scene_min", C.c_float * 3), ("scene_max", C.c_float * 3), ("box_pad", C.c_float),
@@ -89,10 +94,13 @@ SYMBOLS = {
     "lrc_set_gather": (_i32, [_vp, C.POINTER(Gather)]),
     "lrc_gen_rays_single_axis": (_i32, [_vp, _vp, _i64, C.POINTER(SingleAxis), _vp, _vp]),
     "lrc_gen_rays_dual_axis": (_i32, [_vp, _vp, _i64, C.POINTER(DualAxis), C.POINTER(Noise), _vp, _vp, _vp]),
+    "lrc_frame_statistics": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "lrc_pack_ply_records": (_i32, [_vp, _vp, _vp, _vp, _vp, C.c_uint32, _i64, _vp, _vp]),
     "lrc_set_counting": (_i32, [_vp, _i32]),
     "lrc_counters": (_i32, [_vp, C.POINTER(Counters), _i32, _vp]),
     "lrc_launch_count": (_i64, [_vp]),
     "lrc_set_option": (_i32, [_vp, C.c_char_p, _i64]),
+    "lrc_kernel_times": (_i32, [_vp, C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(C.c_int32)]),
 }
 
 _lib = None

@@ -237,6 +237,12 @@ class Context:
     def set_option(self, key: str, value: int) -> None:
         nat.check(self._h, self._lib.lrc_set_option(self._h, key.encode(), int(value)))
 
+    def kernel_times(self) -> dict:
+        """Device time (ms) of k_trace and of the compaction kernels of the last scan (option ``kernel_timing``)."""
+        tr, cp, n = C.c_double(0), C.c_double(0), C.c_int32(0)
+        nat.check(self._h, self._lib.lrc_kernel_times(self._h, C.byref(tr), C.byref(cp), C.byref(n)))
+        return {"trace_ms": tr.value, "compact_ms": cp.value, "trace_launches": n.value}
+
     # ---- scene ----
     def set_mesh_arrays(self, verts, tris, labels=None) -> None:
         """Upload float32 vertices / int32 indices / uint32 labels and build the LBVH on the GPU."""

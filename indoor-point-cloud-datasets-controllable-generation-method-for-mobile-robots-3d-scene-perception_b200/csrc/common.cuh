@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <vector>
 
 #include "../../include/lrc.h"
 
@@ -61,9 +62,19 @@ struct lrc_ctx {
     } gather;
     int64_t opt_gather_chunks = 4;
 
+    // ---- post-processing (post.cu) ----
+    void* post_scratch = nullptr;
+    size_t post_scratch_bytes = 0;
+
     // ---- measurement ----
     unsigned long long* d_counters = nullptr;   // rays, nodes, tris, hits
     int counting = 0;
+    // per-kernel CUDA-event timing of the last scan call (option "kernel_timing"): 4 events per pose chunk,
+    // [before k_trace, after k_trace] on the caller's stream, [before k_scan_counts, after k_compact] on the
+    // stream the compaction runs on
+    int opt_kernel_timing = 0;
+    std::vector<cudaEvent_t> kt_events;
+    size_t kt_used = 0;
 
     // ---- options ----
     int64_t opt_block = 128;            // threads per traversal block

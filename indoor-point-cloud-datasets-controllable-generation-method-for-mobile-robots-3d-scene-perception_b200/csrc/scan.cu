@@ -335,13 +335,14 @@ struct GatherTargets {
     int64_t point_base, frame_base, capacity;
 };
 
+// Launched with the block size k_trace used (one keep count per block of rays).
 template <bool GATHER>
 __global__ void __launch_bounds__(TRACE_THREADS) k_compact(CompactParams q, const __grid_constant__ GatherTargets gt)
 {
     __shared__ int s_warp[TRACE_THREADS / 32];
     const long long run0 = *q.run_in;
     const unsigned blk_base = q.base[blockIdx.x];
-    const int64_t i = (int64_t)blockIdx.x * TRACE_THREADS + threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float4 h = make_float4(0.f, 0.f, 0.f, __uint_as_float(LRC_MISS_ID));
     double inc = 0.0;
     if (i < q.n) {
@@ -407,15 +408,25 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
                  float* t_hit, uint32_t* prim, cudaStream_t stream)
 {
     if (n <= 0) return LRC_OK;
-    const int TB = TRACE_THREADS;
+    const int TB = DENSE ? TRACE_THREADS : (int)ctx->opt_block;
     const unsigned grid = (unsigned)((n + TB - 1) / TB);
     const int has_tris = ctx->T > 0;
 #define LRC_LAUNCH_TRACE(COUNT, VARIANT) \
     k_trace<MODE, COUNT, DENSE, VARIANT><<<grid, TB, 0, stream>>>(g, fm, ctx->nodes, ctx->tris, n, has_tris, hp, inc, block_count, t_hit, prim, ctx->d_counters)
     if (ctx->counting) {
-        if (ctx->opt_variant == 0) LRC_LAUNCH_TRACE(true, 0); else LRC_LAUNCH_TRACE(true, 1);
+        switch (ctx->opt_variant) {
+            case 0: LRC_LAUNCH_TRACE(true, 0); break;
+            case 1: LRC_LAUNCH_TRACE(true, 1); break;
+            case 2: LRC_LAUNCH_TRACE(true, 2); break;
+            default: LRC_LAUNCH_TRACE(true, 3); break;
+        }
     } else {
-        if (ctx->opt_variant == 0) LRC_LAUNCH_TRACE(false, 0); else LRC_LAUNCH_TRACE(false, 1);
+        switch (ctx->opt_variant) {
+            case 0: LRC_LAUNCH_TRACE(false, 0); break;
+            case 1: LRC_LAUNCH_TRACE(false, 1); break;
+            case 2: LRC_LAUNCH_TRACE(false, 2); break;
+            default: LRC_LAUNCH_TRACE(false, 3); break;
+        }
     }
 #undef LRC_LAUNCH_TRACE
     LRC_CHECK_LAUNCH(ctx, "k_trace");
@@ -459,7 +470,8 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
     const bool piped = n_chunks > 1;
     const int n_slots = piped ? 2 : 1;
     const int64_t chunk_rays = frames_per_chunk * N;
-    const int64_t max_blocks = (chunk_rays + TRACE_THREADS - 1) / TRACE_THREADS;
+    const int TB = (int)ctx->opt_block;
+    const int64_t max_blocks = (chunk_rays + TB - 1) / TB;
     const bool want_inc = out->incident_deg != nullptr && max_range >= 0.0;
     const size_t hp_bytes = align_up(sizeof(float4) * (size_t)chunk_rays, 256);
     const size_t inc_bytes = want_inc ? align_up(sizeof(double) * (size_t)chunk_rays, 256) : 0;
@@ -486,6 +498,15 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
         LRC_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[3], stream));      // aux must see the memset of run[0] and the tables
         LRC_CUDA(ctx, cudaStreamWaitEvent(aux, ctx->pipe_ev[3], 0));
     }
+    const bool timing = ctx->opt_kernel_timing != 0;
+    if (timing) {
+        ctx->kt_used = 0;
+        while (ctx->kt_events.size() < (size_t)(4 * n_chunks)) {
+            cudaEvent_t e;
+            LRC_CUDA(ctx, cudaEventCreate(&e));
+            ctx->kt_events.push_back(e);
+        }
+    }
     FrameMath fm;
     fm.max_range = max_range;
     fm.cx = h_center ? h_center[0] : 0.0; fm.cy = h_center ? h_center[1] : 0.0; fm.cz = h_center ? h_center[2] : 0.0;
@@ -501,19 +522,22 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
         const int64_t f0 = c * frames_per_chunk;
         const int64_t nf = (f0 + frames_per_chunk <= P) ? frames_per_chunk : P - f0;
         const int64_t n = nf * N;
-        const int64_t nb = (n + TRACE_THREADS - 1) / TRACE_THREADS;
+        const int64_t nb = (n + TB - 1) / TB;
         float4* hp = (float4*)((char*)ctx->scratch + slot_bytes * slot);
         double* inc = want_inc ? (double*)((char*)ctx->scratch + slot_bytes * slot + hp_bytes) : nullptr;
         unsigned* counts = (unsigned*)(b2 + 2 * cnt_bytes * slot);
         unsigned* base = (unsigned*)(b2 + 2 * cnt_bytes * slot + cnt_bytes);
         g.pose0 = f0;
         if (piped && c >= 2) LRC_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->pipe_ev[slot], 0));   // slot free again?
+        if (timing) LRC_CUDA(ctx, cudaEventRecord(ctx->kt_events[4 * c + 0], stream));
         if ((rc = launch_trace<MODE, false>(ctx, g, fm, n, hp, inc, counts, nullptr, nullptr, stream))) return rc;
+        if (timing) LRC_CUDA(ctx, cudaEventRecord(ctx->kt_events[4 * c + 1], stream));
         if (piped) {
             LRC_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[2], stream));
             LRC_CUDA(ctx, cudaStreamWaitEvent(aux, ctx->pipe_ev[2], 0));
         }
         const bool last = (c == n_chunks - 1);
+        if (timing) LRC_CUDA(ctx, cudaEventRecord(ctx->kt_events[4 * c + 2], aux));
         k_scan_counts<<<1, 1024, 0, aux>>>(counts, base, nb, run + c, run + c + 1, last ? out->frame_offset + P : nullptr);
         LRC_CHECK_LAUNCH(ctx, "k_scan_counts");
         CompactParams q;
@@ -523,9 +547,10 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
         q.out = *out;
         if (!want_inc) q.out.incident_deg = nullptr;
         if (ctx->T == 0) q.out.label = nullptr;
-        if (gather) k_compact<true><<<(unsigned)nb, TRACE_THREADS, 0, aux>>>(q, gt);
-        else k_compact<false><<<(unsigned)nb, TRACE_THREADS, 0, aux>>>(q, gt);
+        if (gather) k_compact<true><<<(unsigned)nb, TB, 0, aux>>>(q, gt);
+        else k_compact<false><<<(unsigned)nb, TB, 0, aux>>>(q, gt);
         LRC_CHECK_LAUNCH(ctx, "k_compact");
+        if (timing) { LRC_CUDA(ctx, cudaEventRecord(ctx->kt_events[4 * c + 3], aux)); ctx->kt_used = (size_t)(4 * (c + 1)); }
         if (piped) LRC_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[slot], aux));
     }
     if (piped) {   // the caller's stream owns the result: join the auxiliary stream back
@@ -626,9 +651,10 @@ extern "C" void lrc_destroy(lrc_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaFree(ctx->nodes); cudaFree(ctx->tris); cudaFree(ctx->labels);
     cudaFree(ctx->scratch); cudaFree(ctx->scratch2); cudaFree(ctx->tables); cudaFree(ctx->d_counters);
-    cudaFree(ctx->host_dev); cudaFree(ctx->mesh_dev);
+    cudaFree(ctx->host_dev); cudaFree(ctx->mesh_dev); cudaFree(ctx->post_scratch);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->scratch_event) cudaEventDestroy(ctx->scratch_event);
+    for (cudaEvent_t e : ctx->kt_events) cudaEventDestroy(e);
     if (ctx->s_aux) { cudaStreamDestroy(ctx->s_aux); for (int k = 0; k < 4; ++k) cudaEventDestroy(ctx->pipe_ev[k]); }
     for (size_t i = 0; i < ctx->n_events; ++i) cudaEventDestroy(ctx->events[i]);
     free(ctx->events);
@@ -663,13 +689,40 @@ extern "C" int lrc_counters(lrc_ctx* ctx, lrc_counters_t* h_out, int reset, void
     return LRC_OK;
 }
 
+extern "C" int lrc_kernel_times(lrc_ctx* ctx, double* h_trace_ms, double* h_compact_ms, int32_t* h_launches)
+{
+    if (!ctx || !h_trace_ms || !h_compact_ms) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_kernel_times: NULL argument");
+    if (!ctx->opt_kernel_timing || ctx->kt_used == 0)
+        return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_kernel_times: enable option kernel_timing and run a scan first");
+    LRC_CUDA(ctx, cudaSetDevice(ctx->device));
+    double tr = 0.0, cp = 0.0;
+    for (size_t c = 0; c < ctx->kt_used / 4; ++c) {
+        float a = 0.f, b = 0.f;
+        LRC_CUDA(ctx, cudaEventSynchronize(ctx->kt_events[4 * c + 1]));
+        LRC_CUDA(ctx, cudaEventSynchronize(ctx->kt_events[4 * c + 3]));
+        LRC_CUDA(ctx, cudaEventElapsedTime(&a, ctx->kt_events[4 * c + 0], ctx->kt_events[4 * c + 1]));
+        LRC_CUDA(ctx, cudaEventElapsedTime(&b, ctx->kt_events[4 * c + 2], ctx->kt_events[4 * c + 3]));
+        tr += a; cp += b;
+    }
+    *h_trace_ms = tr;
+    *h_compact_ms = cp;
+    if (h_launches) *h_launches = (int32_t)(ctx->kt_used / 4);
+    return LRC_OK;
+}
+
 extern "C" int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value)
 {
     if (!ctx || !key) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_option: NULL argument");
     if (!strcmp(key, "chunk_rays")) { if (value < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "chunk_rays must be >= 1"); ctx->opt_chunk_rays = value; return LRC_OK; }
     if (!strcmp(key, "gather_chunks")) { if (value < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "gather_chunks must be >= 1"); ctx->opt_gather_chunks = value; return LRC_OK; }
+    if (!strcmp(key, "block")) {
+        if (value != 32 && value != 64 && value != 128) return lrc_fail(ctx, LRC_ERR_INVALID, "block must be 32, 64 or 128");
+        ctx->opt_block = value;
+        return LRC_OK;
+    }
+    if (!strcmp(key, "kernel_timing")) { ctx->opt_kernel_timing = value != 0; ctx->kt_used = 0; return LRC_OK; }
     if (!strcmp(key, "variant")) {
-        if (value < 0 || value > 1) return lrc_fail(ctx, LRC_ERR_INVALID, "variant must be 0 or 1");
+        if (value < 0 || value > 3) return lrc_fail(ctx, LRC_ERR_INVALID, "variant must be 0..3");
         ctx->opt_variant = value;
         return LRC_OK;
     }

@@ -84,6 +84,20 @@ __device__ __forceinline__ bool slab_ch(float cx, float cy, float cz, float hx, 
     return t0 <= t1;
 }
 
+// 256-bit global loads (sm_100+: LDG.E.256): a 64 B node record is two of them instead of 3 x 128 + 1 x 64 bits, a 48 B
+// triangle record one 256 + one 128.  Halves the LSU instructions and L1 wavefronts per record; the record arrays are
+// cudaMalloc'ed (256 B aligned) and records are 64 / 48 B, so a node is always 32 B aligned and a triangle 16 B aligned
+// (its first 32 bytes are fetched as 2 x 128 when the slot is odd).
+struct F8 { float4 a, b; };
+__device__ __forceinline__ F8 ldg256(const void* p)
+{
+    F8 r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+        : "l"(p));
+    return r;
+}
+
 #define LRC_SENTINEL ((int)0x80000000)   // a "leaf" link no tree contains: ~0x80000000 = 0x7fffffff slots
 
 __device__ __forceinline__ void leaf_test(const float4* __restrict__ tris, int link, float ox, float oy, float oz, float dx,
@@ -99,13 +113,20 @@ __device__ __forceinline__ void leaf_test(const float4* __restrict__ tris, int l
 }
 
 // One step at an inner node: returns the next link (child to descend into, or a popped entry, or the sentinel).
-template <bool COUNT>
+template <bool COUNT, bool WIDE>
 __device__ __forceinline__ int inner_step(const float4* __restrict__ nodes, int cur, const RaySlab& s, float best_t,
                                           int* stack, int& sp, unsigned& n_nodes)
 {
     const float4* np = nodes + 4 * (int64_t)cur;
-    const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
-    const float2 n3 = __ldg(reinterpret_cast<const float2*>(np + 3));
+    float4 n0, n1, n2;
+    float2 n3;
+    if (WIDE) {
+        const F8 lo = ldg256(np), hi = ldg256(np + 2);
+        n0 = lo.a; n1 = lo.b; n2 = hi.a; n3 = make_float2(hi.b.x, hi.b.y);
+    } else {
+        n0 = __ldg(np + 0); n1 = __ldg(np + 1); n2 = __ldg(np + 2);
+        n3 = __ldg(reinterpret_cast<const float2*>(np + 3));
+    }
     if (COUNT) ++n_nodes;
     float t0, t1;
     const bool h0 = slab_ch(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, s, best_t, t0);
@@ -121,8 +142,9 @@ __device__ __forceinline__ int inner_step(const float4* __restrict__ nodes, int 
     return sp > 0 ? stack[--sp] : LRC_SENTINEL;
 }
 
-// Stack-based closest-hit traversal.  VARIANT 0: one node (inner or leaf) per loop trip ("if-if").
-// VARIANT 1: "while-while" -- run down inner nodes until a leaf (or the end) is reached, then test the leaf.
+// Stack-based closest-hit traversal.  VARIANT bit 0: 0 = one node (inner or leaf) per loop trip ("if-if"),
+// 1 = "while-while" -- run down inner nodes until a leaf (or the end) is reached, then test the leaf.
+// VARIANT bit 1: node records fetched with 256-bit loads.
 template <int VARIANT, bool COUNT>
 __device__ __forceinline__ void trace_ray(const float4* __restrict__ nodes, const float4* __restrict__ tris, float ox,
                                           float oy, float oz, float dx, float dy, float dz, float& best_t,
@@ -134,10 +156,11 @@ __device__ __forceinline__ void trace_ray(const float4* __restrict__ nodes, cons
     int stack[LRC_STACK_DEPTH];
     int sp = 0;
     int cur = 0;
-    if (VARIANT == 0) {
+    constexpr bool WIDE = (VARIANT & 2) != 0;
+    if ((VARIANT & 1) == 0) {
         while (cur != LRC_SENTINEL) {
             if (cur >= 0) {
-                cur = inner_step<COUNT>(nodes, cur, s, best_t, stack, sp, n_nodes);
+                cur = inner_step<COUNT, WIDE>(nodes, cur, s, best_t, stack, sp, n_nodes);
             } else {
                 if (COUNT) ++n_tris;
                 leaf_test(tris, cur, ox, oy, oz, dx, dy, dz, best_t, best_id);
@@ -146,7 +169,7 @@ __device__ __forceinline__ void trace_ray(const float4* __restrict__ nodes, cons
         }
     } else {
         while (cur != LRC_SENTINEL) {
-            while (cur >= 0) cur = inner_step<COUNT>(nodes, cur, s, best_t, stack, sp, n_nodes);
+            while (cur >= 0) cur = inner_step<COUNT, WIDE>(nodes, cur, s, best_t, stack, sp, n_nodes);
             if (cur != LRC_SENTINEL) {
                 if (COUNT) ++n_tris;
                 leaf_test(tris, cur, ox, oy, oz, dx, dy, dz, best_t, best_id);
