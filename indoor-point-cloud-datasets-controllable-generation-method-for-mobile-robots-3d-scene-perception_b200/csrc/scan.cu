@@ -267,6 +267,7 @@ __global__ void k_brute(const float* __restrict__ rays, int64_t n, const float4*
 // The reference's boolean-mask indexing keeps ray order (raycast_engine_cpu.py:71,:97), so the compaction must be
 // order-preserving: per-block keep counts (written by k_trace) -> exclusive scan -> each block scatters its kept
 // rays at base + warp-ballot prefix.  No atomics decide positions, so the output order is deterministic.
+constexpr int SC_ITEMS = 16;   // counts per thread per trip (4 x uint4): 16384 counts per trip of the single block
 __global__ void __launch_bounds__(1024) k_scan_counts(const unsigned* __restrict__ counts, unsigned* __restrict__ base,
                                                       int64_t nb, const long long* __restrict__ run_in,
                                                       long long* __restrict__ run_out, int64_t* __restrict__ frame_offset_last)
@@ -276,10 +277,23 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const unsigned* __restrict
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry = 0u;
     __syncthreads();
-    for (int64_t b0 = 0; b0 < nb; b0 += 1024) {
-        const int64_t i = b0 + threadIdx.x;
-        const unsigned v = i < nb ? counts[i] : 0u;
-        unsigned incl = v;
+    for (int64_t b0 = 0; b0 < nb; b0 += 1024 * SC_ITEMS) {
+        const int64_t i0 = b0 + (int64_t)threadIdx.x * SC_ITEMS;
+        unsigned v[SC_ITEMS];
+        if (i0 + SC_ITEMS <= nb) {      // the arrays are 256 B aligned and i0 is a multiple of 16
+#pragma unroll
+            for (int k = 0; k < SC_ITEMS / 4; ++k) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(counts + i0) + k);
+                v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < SC_ITEMS; ++k) v[k] = i0 + k < nb ? counts[i0 + k] : 0u;
+        }
+        unsigned mine = 0u;
+#pragma unroll
+        for (int k = 0; k < SC_ITEMS; ++k) mine += v[k];
+        unsigned incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -297,10 +311,26 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const unsigned* __restrict
             warp_sums[lane] = si - sv;
         }
         __syncthreads();
-        const unsigned excl = incl - v + warp_sums[w] + carry;
-        if (i < nb) base[i] = excl;
+        unsigned run = incl - mine + warp_sums[w] + carry;
+        if (i0 + SC_ITEMS <= nb) {
+#pragma unroll
+            for (int k = 0; k < SC_ITEMS / 4; ++k) {
+                uint4 q;
+                q.x = run; run += v[4 * k];
+                q.y = run; run += v[4 * k + 1];
+                q.z = run; run += v[4 * k + 2];
+                q.w = run; run += v[4 * k + 3];
+                reinterpret_cast<uint4*>(base + i0)[k] = q;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < SC_ITEMS; ++k) {
+                if (i0 + k < nb) base[i0 + k] = run;
+                run += v[k];
+            }
+        }
         __syncthreads();
-        if (threadIdx.x == 1023) carry = excl + v;
+        if (threadIdx.x == 1023) carry = run;
         __syncthreads();
     }
     if (threadIdx.x == 0) {
