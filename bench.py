@@ -310,6 +310,8 @@ def run_ours(args):
         from lrc_b200.distributed import PeerGather
         peer = PeerGather(ctx, cap_per_rank=P * n_frame, frames_per_rank=P)
         ctx.set_option("gather_chunks", args.gather_chunks)
+        if args.push_blocks:
+            ctx.set_option("push_blocks", args.push_blocks)
         peer.enable()
 
     def one_step():
@@ -454,8 +456,8 @@ def run_ours(args):
                        "poses_per_gpu": P, "poses_total": int(len(poses_all)), "parallelism": f"pose-sharded x{world}, replicated BVH",
                        "l2": "flushed between timed iterations (256 MiB fill)", "noise": bool(w["noise"]),
                        "collective": ("none" if world == 1 else
-                                      f"fused in the compaction kernel: xyz|label|frame_offset stored to all {world} ranks over NVLink peer memory, "
-                                      f"{args.gather_chunks} chunks overlapped with traversal, inside the step" if args.gather == "p2p" else
+                                      f"all-gather over NVLink peer memory: each compacted pose chunk's xyz|label|frame_offset is pushed to all {world} ranks by an "
+                                      f"exchange kernel (16 B vector stores) while the next chunk is traversed; {args.gather_chunks} chunks, inside the step" if args.gather == "p2p" else
                                       f"NCCL all-gather of xyz|label|frame_offset blocks, {args.gather_chunks} chunks, overlapped with traversal, inside the step")},
             "frames_per_s": round(len(poses_all) / (ms_per_step * 1e-3), 1),
             "wall_ms_per_step_incl_flush": round(wall / args.steps * 1e3, 4),
@@ -485,6 +487,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N>1: how the clouds are exchanged")
     ap.add_argument("--gather-chunks", type=int, default=4, help="N>1: pose chunks per rank for the overlapped all-gather")
+    ap.add_argument("--push-blocks", type=int, default=None, help="N>1: blocks per target of the exchange kernel")
     ap.add_argument("--e2e-chunk", type=int, default=None, help="poses per chunk of the pipelined e2e path")
     ap.add_argument("--variant", type=int, default=None, help="traversal kernel variant (lrc_set_option)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")

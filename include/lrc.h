@@ -167,14 +167,16 @@ int lrc_scan_dual_axis_host(lrc_ctx* ctx, const double* h_poses, int64_t P, cons
 int lrc_set_mesh_host(lrc_ctx* ctx, const float* h_verts, int64_t V, const int32_t* h_tris, int64_t T,
                       const uint32_t* h_tri_label);
 
-/* ---- multi-GPU: fused compaction + all-gather over NVLink peer memory ------------------------ */
+/* ---- multi-GPU: all-gather of the compacted clouds over NVLink peer memory, overlapped with traversal -------- */
 /* The reference has no multi-process path; this is the exchange step of the pose-sharded run.
  * A peer buffer is plain device memory whose CUDA IPC handle other ranks open; lrc_set_gather names up to 16
- * target buffers (this GPU's own and the peers' mapped ones).  While targets are set, every scan's compaction kernel
- * stores each kept point's xyz and label into EVERY target at point_base + position, and the frame offsets at
- * frame_base + frame (+ the closing entry at frame_base + P), on top of the regular lrc_out.  The stores to peers
- * travel over NVLink while the next pose chunk is being traversed.  Callers synchronise their stream and then
- * barrier across ranks before reading. */
+ * target buffers (this GPU's own and the peers' mapped ones).  While targets are set, every scan cuts the trajectory
+ * into pose chunks ("gather_chunks"); as soon as a chunk has been compacted locally, an exchange kernel copies that
+ * chunk's xyz and label slices into EVERY target at point_base + position with 16-byte vector stores, and the chunk's
+ * frame offsets at frame_base + frame (+ the closing entry at frame_base + P).  Slice bounds are read on the device
+ * (no host round trip); the stores to peers travel over NVLink while the next chunk is being traversed.  point_base
+ * should be a multiple of 4 (keeps source and destination congruent modulo 16 bytes).  Callers synchronise their
+ * stream and then barrier across ranks before reading.  The scan's lrc_out must carry a label array. */
 #define LRC_MAX_GATHER_TARGETS 16
 typedef struct { unsigned char bytes[64]; } lrc_ipc_handle;
 typedef struct {
@@ -223,6 +225,33 @@ int lrc_frame_statistics(lrc_ctx* ctx, const float* xyz, const double* incident_
  *    16-byte aligned, device.  The caller prepends the text header (:621-632) and writes the bytes. */
 int lrc_pack_ply_records(lrc_ctx* ctx, const float* xyz, const uint32_t* label, const uint32_t* prim_id,
                          const uint32_t* tri_rgb, uint32_t default_rgb, int64_t M, uint8_t* out, void* stream);
+
+/* ---- the caller that produces the poses: coverage-trajectory planner support --------------- */
+/* == the vertex set AutoTrajectoryGenerator._is_point_inside_mesh scans for every query point
+ *    (trajectory/auto_trajectory_generator.py:220-238), binned once on a 2-D grid of `cell` metres.
+ *    verts: V x 3 float64 (the legacy mesh's vertices, NOT rounded to float32), device.  Kept until the next build. */
+int lrc_collision_index_build(lrc_ctx* ctx, const double* verts, int64_t V, double cell, void* stream);
+/* state[q] = 0  the robot cube [p - half, p + half] leaves h_bounds = {x_min, x_max, y_min, y_max, z_min, z_max}
+ *               (_is_point_in_room_bounds, :204-217; h_bounds NULL = no bounds test)
+ *          = 1  some vertex lies inside the closed cube (_is_point_inside_mesh, :220-238)
+ *          = 2  free.                         pts: Q x 3 float64, device; state: Q bytes, device. */
+int lrc_collision_query(lrc_ctx* ctx, const double* pts, int64_t Q, double half, const double* h_bounds,
+                        uint8_t* state, void* stream);
+/* == _build_connectivity_graph (:245-258) for grid samples (xs[ix], ys[iy], z) in the reference's x-major order:
+ *    free_index[ix * ny + iy] = rank of the cell among the free ones (state == 2) or -1; CSR rows = free points,
+ *    columns = the free points j != i with ||p_i - p_j|| <= max_dist, ascending.  `window` = how many grid steps
+ *    around a cell are examined (ceil(max_dist / step) + 1 is always enough).  h_counts[0] = number of free points,
+ *    h_counts[1] = number of edges.  row_ptr: capacity nx*ny + 1; col: capacity col_capacity (LRC_ERR_CAPACITY if
+ *    smaller than the edge count, with h_counts already set).  All arrays device except h_counts.  Synchronises. */
+int lrc_grid_connectivity(lrc_ctx* ctx, const double* xs, int32_t nx, const double* ys, int32_t ny, const uint8_t* state,
+                          double max_dist, int32_t window, int32_t* free_index, int32_t* row_ptr, int32_t* col,
+                          int64_t col_capacity, int64_t* h_counts, void* stream);
+/* == _a_star_search (:413-473) over a CSR graph of points, all HOST arrays (the reference's search is host code too):
+ *    Euclidean edge costs and heuristic, closed nodes never reopened.  Ties on f are broken by the smaller node index
+ *    (the reference's tie-break is CPython's set iteration order), so equal-cost paths may differ in shape, never in
+ *    cost.  *h_path_len = 0 when no path exists. */
+int lrc_astar(const int32_t* h_row_ptr, const int32_t* h_col, const double* h_pts, int32_t n, int32_t start, int32_t end,
+              int32_t* h_path, int32_t path_capacity, int32_t* h_path_len, double* h_cost);
 
 /* ---- measurement ---------------------------------------------------------------------------- */
 /* Work counters, accumulated by cast/scan calls while counting is enabled (a separate, slower

@@ -19,7 +19,7 @@ from .lidar import (DualAxisLidar, DualAxisLidarIntrinsics, Indoor8LineLidarIntr
 from .raycast_engine import RaycastEngineBase, RaycastEngineGPU
 from .post import (ScanQuality, SimulationStats, frame_statistics, read_labeled_ply, scan_quality, simulation_stats,
                    write_labeled_ply)
-from .trajectory import Waypoint, poses_from_waypoints, shard_range
+from .trajectory import AutoTrajectoryGenerator, TrajectoryQuality, Waypoint, poses_from_waypoints, shard_range
 
 __version__ = "0.1.0"
 
@@ -32,5 +32,5 @@ __all__ = [
     "LidarIntrinsics", "Indoor8LineLidarIntrinsics", "DualAxisLidarIntrinsics", "IndoorLidar", "DualAxisLidar",
     "create_lidar", "get_lidar_type",
     "RaycastEngineBase", "RaycastEngineGPU",
-    "Waypoint", "poses_from_waypoints", "shard_range",
+    "Waypoint", "poses_from_waypoints", "shard_range", "AutoTrajectoryGenerator", "TrajectoryQuality",
 ]

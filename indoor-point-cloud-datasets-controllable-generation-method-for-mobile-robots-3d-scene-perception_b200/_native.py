@@ -96,6 +96,10 @@ SYMBOLS = {
     "lrc_gen_rays_dual_axis": (_i32, [_vp, _vp, _i64, C.POINTER(DualAxis), C.POINTER(Noise), _vp, _vp, _vp]),
     "lrc_frame_statistics": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "lrc_pack_ply_records": (_i32, [_vp, _vp, _vp, _vp, _vp, C.c_uint32, _i64, _vp, _vp]),
+    "lrc_collision_index_build": (_i32, [_vp, _vp, _i64, _dbl, _vp]),
+    "lrc_collision_query": (_i32, [_vp, _vp, _i64, _dbl, C.POINTER(_dbl), _vp, _vp]),
+    "lrc_grid_connectivity": (_i32, [_vp, _vp, C.c_int32, _vp, C.c_int32, _vp, _dbl, C.c_int32, _vp, _vp, _vp, _i64, C.POINTER(_i64), _vp]),
+    "lrc_astar": (_i32, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_int32, C.POINTER(C.c_int32), C.POINTER(_dbl)]),
     "lrc_set_counting": (_i32, [_vp, _i32]),
     "lrc_counters": (_i32, [_vp, C.POINTER(Counters), _i32, _vp]),
     "lrc_launch_count": (_i64, [_vp]),

@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "liblrc.so")
-SOURCES = ["bvh_build.cu", "scan.cu", "post.cu"]
+SOURCES = ["bvh_build.cu", "scan.cu", "post.cu", "plan.cu"]
 HEADERS = ["common.cuh", "traverse.cuh", os.path.join("..", "..", "include", "lrc.h")]
 
 NVCC_FLAGS = [

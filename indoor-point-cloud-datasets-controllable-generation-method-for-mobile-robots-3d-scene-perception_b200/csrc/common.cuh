@@ -61,6 +61,16 @@ struct lrc_ctx {
         int64_t point_base = 0, frame_base = 0, capacity = 0;
     } gather;
     int64_t opt_gather_chunks = 4;
+    int64_t opt_push_blocks = 16;       // blocks per target of the k_push exchange kernel
+
+    // ---- planner support (plan.cu): binned vertex index ----
+    bool ci_ready = false;
+    int64_t ci_V = 0;
+    void* ci_meta = nullptr; size_t ci_meta_bytes = 0;
+    void* ci_start = nullptr; size_t ci_start_bytes = 0;
+    void* ci_sorted = nullptr; size_t ci_sorted_bytes = 0;
+    double ci_ox = 0, ci_oy = 0, ci_cell = 0;
+    int ci_nbx = 0, ci_nby = 0;
 
     // ---- post-processing (post.cu) ----
     void* post_scratch = nullptr;

@@ -354,20 +354,8 @@ struct CompactParams {
     lrc_out out;
 };
 
-// Peer targets of the fused compaction + all-gather (lrc_set_gather): the same record is stored into every
-// target's buffer -- local HBM or another GPU's HBM mapped over NVLink (cudaIpcOpenMemHandle) -- at
-// point_base + position, so that after the kernel every GPU holds every rank's slice of the cloud.
-struct GatherTargets {
-    int n;
-    float* xyz[LRC_MAX_GATHER];
-    uint32_t* label[LRC_MAX_GATHER];
-    int64_t* frame_offset[LRC_MAX_GATHER];
-    int64_t point_base, frame_base, capacity;
-};
-
 // Launched with the block size k_trace used (one keep count per block of rays).
-template <bool GATHER>
-__global__ void __launch_bounds__(TRACE_THREADS) k_compact(CompactParams q, const __grid_constant__ GatherTargets gt)
+__global__ void __launch_bounds__(TRACE_THREADS) k_compact(CompactParams q)
 {
     __shared__ int s_warp[TRACE_THREADS / 32];
     const long long run0 = *q.run_in;
@@ -394,33 +382,80 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_compact(CompactParams q, cons
         const int64_t gidx = q.ray0 + i;
         const int64_t frame = gidx / q.N;
         const int64_t r = gidx - frame * q.N;
-        const bool closes = gidx == q.total_rays - 1;      // this thread owns the last ray of the call
         if (r == 0) q.out.frame_offset[frame] = pos;
-        uint32_t lab = 0u;
-        if (keep && (q.out.label || GATHER) && q.labels) lab = __ldg(q.labels + id);
         if (keep && pos < q.out.capacity) {
             q.out.xyz[3 * pos + 0] = h.x;
             q.out.xyz[3 * pos + 1] = h.y;
             q.out.xyz[3 * pos + 2] = h.z;
             if (q.out.incident_deg) q.out.incident_deg[pos] = inc;
             if (q.out.prim_id) q.out.prim_id[pos] = id;
-            if (q.out.label) q.out.label[pos] = lab;
+            if (q.out.label) q.out.label[pos] = q.labels ? __ldg(q.labels + id) : 0u;
             if (q.out.ray_idx) q.out.ray_idx[pos] = (uint32_t)r;
         }
-        if (GATHER) {
-            const long long gp = gt.point_base + pos;
-#pragma unroll 1
-            for (int k = 0; k < gt.n; ++k) {
-                if (keep && pos < gt.capacity) {
-                    float* x = gt.xyz[k] + 3 * gp;
-                    x[0] = h.x; x[1] = h.y; x[2] = h.z;
-                    gt.label[k][gp] = lab;
-                }
-                if (r == 0) gt.frame_offset[k][gt.frame_base + frame] = gp;
-                if (closes) gt.frame_offset[k][gt.frame_base + q.P] = gp + (keep ? 1 : 0);
-            }
-        }
     }
+}
+
+// ---- multi-GPU exchange: push a finished chunk of the compacted cloud into every rank's gather buffer ----------------
+// Peer targets (lrc_set_gather): buffers in local HBM or in another GPU's HBM mapped over NVLink (cudaIpcOpenMemHandle).
+// After chunk c has been compacted locally, k_push copies its slice [run[c], run[c+1]) of xyz and label -- and the frame
+// offsets of the chunk's frames, rebased -- to point_base + position in EVERY target with 16-byte vector loads and
+// stores, so each warp store is 512 contiguous bytes on the wire.  (The first version stored 4 bytes at a time from inside
+// the compaction kernel: 32 remote stores per point at 8 GPUs, 0.8 ms per chunk; see profiles/.)  The slice bounds are
+// read from device memory, so nothing returns to the host; the kernel runs on the auxiliary stream while the next chunk
+// is traversed on the caller's stream.
+struct GatherTargets {
+    int n;
+    float* xyz[LRC_MAX_GATHER];
+    uint32_t* label[LRC_MAX_GATHER];
+    int64_t* frame_offset[LRC_MAX_GATHER];
+    int64_t point_base, frame_base, capacity;
+};
+
+struct PushParams {
+    const float* xyz;              // local compacted outputs of this call (lrc_out)
+    const uint32_t* label;
+    const int64_t* frame_offset;
+    const long long* run;          // run[0], run[1]: first and one-past-last point of the chunk
+    int64_t f0, nf, P;             // frames of the chunk; P = frames of the whole call
+    int last;                      // the chunk that owns the closing frame offset
+};
+
+// copy n 4-byte words src -> dst; both pointers 4-byte aligned and congruent modulo 16 (else word by word)
+__device__ __forceinline__ void push_words(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int64_t n, int64_t tid, int64_t nthreads)
+{
+    if ((((uintptr_t)src) & 15u) != (((uintptr_t)dst) & 15u)) {
+        for (int64_t i = tid; i < n; i += nthreads) dst[i] = __ldcg(src + i);
+        return;
+    }
+    int64_t head = (int64_t)(((16u - (((uintptr_t)src) & 15u)) & 15u) >> 2);
+    if (head > n) head = n;
+    const int64_t nvec = (n - head) >> 2;
+    const int64_t tail0 = head + (nvec << 2);
+    if (tid < head) dst[tid] = __ldcg(src + tid);
+    if (tid < n - tail0) dst[tail0 + tid] = __ldcg(src + tail0 + tid);
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
+    uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+    int64_t i = tid;
+    for (; i + 3 * nthreads < nvec; i += 4 * nthreads) {            // four vectors in flight per thread
+        const uint4 a = __ldcg(s4 + i), b = __ldcg(s4 + i + nthreads), c = __ldcg(s4 + i + 2 * nthreads), d = __ldcg(s4 + i + 3 * nthreads);
+        d4[i] = a; d4[i + nthreads] = b; d4[i + 2 * nthreads] = c; d4[i + 3 * nthreads] = d;
+    }
+    for (; i < nvec; i += nthreads) d4[i] = __ldcg(s4 + i);
+}
+
+constexpr int PUSH_THREADS = 256;
+__global__ void __launch_bounds__(PUSH_THREADS) k_push(PushParams q, const __grid_constant__ GatherTargets gt)
+{
+    const int k = blockIdx.y;                       // target
+    const long long a = q.run[0], b = q.run[1];
+    const int64_t tid = (int64_t)blockIdx.x * PUSH_THREADS + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * PUSH_THREADS;
+    const long long gp = gt.point_base + a;
+    push_words(reinterpret_cast<const uint32_t*>(q.xyz + 3 * a), reinterpret_cast<uint32_t*>(gt.xyz[k] + 3 * gp), 3 * (b - a), tid, nthreads);
+    if (q.label) push_words(q.label + a, gt.label[k] + gp, b - a, tid, nthreads);
+    else for (int64_t i = tid; i < b - a; i += nthreads) gt.label[k][gp + i] = 0u;
+    for (int64_t f = tid; f < q.nf; f += nthreads) gt.frame_offset[k][gt.frame_base + q.f0 + f] = gt.point_base + q.frame_offset[q.f0 + f];
+    if (q.last && tid == 0) gt.frame_offset[k][gt.frame_base + q.P] = gt.point_base + b;
 }
 
 // ---- host-side launch plumbing -----------------------------------------------------------------------
@@ -577,9 +612,16 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
         q.out = *out;
         if (!want_inc) q.out.incident_deg = nullptr;
         if (ctx->T == 0) q.out.label = nullptr;
-        if (gather) k_compact<true><<<(unsigned)nb, TB, 0, aux>>>(q, gt);
-        else k_compact<false><<<(unsigned)nb, TB, 0, aux>>>(q, gt);
+        if (gather && !q.out.label && ctx->T > 0) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_gather: the scan's lrc_out needs a label array");
+        k_compact<<<(unsigned)nb, TB, 0, aux>>>(q);
         LRC_CHECK_LAUNCH(ctx, "k_compact");
+        if (gather) {
+            PushParams pp;
+            pp.xyz = out->xyz; pp.label = q.out.label; pp.frame_offset = out->frame_offset; pp.run = run + c;
+            pp.f0 = f0; pp.nf = nf; pp.P = P; pp.last = last ? 1 : 0;
+            k_push<<<dim3((unsigned)ctx->opt_push_blocks, (unsigned)gt.n), PUSH_THREADS, 0, aux>>>(pp, gt);
+            LRC_CHECK_LAUNCH(ctx, "k_push");
+        }
         if (timing) { LRC_CUDA(ctx, cudaEventRecord(ctx->kt_events[4 * c + 3], aux)); ctx->kt_used = (size_t)(4 * (c + 1)); }
         if (piped) LRC_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[slot], aux));
     }
@@ -682,6 +724,7 @@ extern "C" void lrc_destroy(lrc_ctx* ctx)
     cudaFree(ctx->nodes); cudaFree(ctx->tris); cudaFree(ctx->labels);
     cudaFree(ctx->scratch); cudaFree(ctx->scratch2); cudaFree(ctx->tables); cudaFree(ctx->d_counters);
     cudaFree(ctx->host_dev); cudaFree(ctx->mesh_dev); cudaFree(ctx->post_scratch);
+    cudaFree(ctx->ci_meta); cudaFree(ctx->ci_start); cudaFree(ctx->ci_sorted);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->scratch_event) cudaEventDestroy(ctx->scratch_event);
     for (cudaEvent_t e : ctx->kt_events) cudaEventDestroy(e);
@@ -744,6 +787,7 @@ extern "C" int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value)
 {
     if (!ctx || !key) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_option: NULL argument");
     if (!strcmp(key, "chunk_rays")) { if (value < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "chunk_rays must be >= 1"); ctx->opt_chunk_rays = value; return LRC_OK; }
+    if (!strcmp(key, "push_blocks")) { if (value < 1 || value > 1024) return lrc_fail(ctx, LRC_ERR_INVALID, "push_blocks must be in [1, 1024]"); ctx->opt_push_blocks = value; return LRC_OK; }
     if (!strcmp(key, "gather_chunks")) { if (value < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "gather_chunks must be >= 1"); ctx->opt_gather_chunks = value; return LRC_OK; }
     if (!strcmp(key, "block")) {
         if (value != 32 && value != 64 && value != 128) return lrc_fail(ctx, LRC_ERR_INVALID, "block must be 32, 64 or 128");

@@ -113,6 +113,14 @@ def box_room(target_tris: int = 50_000, seed: int = 0) -> TriangleMesh:
     return build_mesh(boxes, target_tris, seed)
 
 
+def planner_tight_room(seed: int = 5) -> TriangleMesh:
+    """A 1.4 x 1.6 x 2.5 m closet with a pillar: the planner's coarse 0.2 m grid finds fewer than 10 free points, which
+    sends the reference into its detailed-resolution branch (auto_trajectory_generator.py:151-152,167-202)."""
+    boxes = [Box((0, 0, 0), (1.4, 1.6, 2.5), SEM_WALL, 0, room_shell=True),
+             Box((0.55, 0.75, 0.0), (0.85, 0.85, 2.0), SEM_BOOKCASE, 3)]
+    return build_mesh(boxes, 3000, seed)
+
+
 def box_room_pose() -> np.ndarray:
     """C1's single pose: (3.137, 2.718, 1.0), yaw 0.3 rad."""
     return Waypoint(3.137, 2.718, 1.0, 0.3).to_pose_matrix()

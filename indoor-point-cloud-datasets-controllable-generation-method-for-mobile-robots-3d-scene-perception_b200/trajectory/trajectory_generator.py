@@ -1,12 +1,13 @@
 """
 Pose format of the simulator's frame loop (reference trajectory/trajectory_generator.py:13-44 and
 s3dis_simulator.py:254-257) plus simple seeded trajectories for the synthetic benchmark scenes.
-The reference's coverage planner (auto_trajectory_generator.py) is out of scope.
+The coverage planner lives next door in ``auto_trajectory_generator.py``.
 """
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Iterable, List, Optional, Sequence
+from dataclasses import asdict
+from typing import Any, Dict, Iterable, List, Optional, Sequence
 
 import numpy as np
 
@@ -38,6 +39,20 @@ class Waypoint:
 
     def angle_to(self, other: "Waypoint") -> float:
         return float(np.arctan2(other.y - self.y, other.x - self.x))
+
+
+@dataclass
+class TrajectoryQuality:
+    """Same fields as the reference's ``TrajectoryQuality`` (trajectory_generator.py:60-82)."""
+    coverage_ratio: float
+    path_length: float
+    turn_count: int
+    efficiency: float
+    collision_count: int
+    smoothness: float
+
+    def to_dict(self) -> Dict[str, Any]:
+        return asdict(self)
 
 
 def poses_from_waypoints(waypoints: Iterable[Waypoint]) -> np.ndarray:
