@@ -226,6 +226,21 @@ int lrc_frame_statistics(lrc_ctx* ctx, const float* xyz, const double* incident_
 int lrc_pack_ply_records(lrc_ctx* ctx, const float* xyz, const uint32_t* label, const uint32_t* prim_id,
                          const uint32_t* tri_rgb, uint32_t default_rgb, int64_t M, uint8_t* out, void* stream);
 
+/* ---- 1-nearest-neighbour label / colour transfer -------------------------------------------- */
+/* == NearestNeighbors(n_neighbors=1, algorithm='ball_tree').fit(ref_pts) (scikit-learn, third party; reference
+ *    containers/s3dis_sim_scene.py:413-417 and :536-538).  ref_pts: n x 3 float64, device (the annotated S3DIS points).
+ *    Bins them on a uniform 3-D grid of `cell` metres (0 = automatic); kept until the next build. */
+int lrc_nn_index_build(lrc_ctx* ctx, const double* ref_pts, int64_t n, double cell, void* stream);
+/* == .kneighbors(points) + the gathers colours[indices], labels[indices] (:418-424).  query_xyz: M x 3 float32 (the
+ *    frame's hit points; promoted to float64 like scikit-learn does).  out_index[i] = argmin_j of the float64 reduced
+ *    distance ((dx*dx + dy*dy) + dz*dz), ties -> smaller j; -1 when the index is empty or the query is not finite.
+ *    out_distance (may be NULL): Euclidean distance.  Up to two uint32 attribute tables of the annotated points
+ *    (e.g. sem | ins << 16 and packed rgb) are gathered through the indices when both ref_attr_x and out_attr_x are
+ *    given.  All arrays device. */
+int lrc_nn_query(lrc_ctx* ctx, const float* query_xyz, int64_t M, int32_t* out_index, double* out_distance,
+                 const uint32_t* ref_attr_a, uint32_t* out_attr_a, const uint32_t* ref_attr_b, uint32_t* out_attr_b,
+                 void* stream);
+
 /* ---- the caller that produces the poses: coverage-trajectory planner support --------------- */
 /* == the vertex set AutoTrajectoryGenerator._is_point_inside_mesh scans for every query point
  *    (trajectory/auto_trajectory_generator.py:220-238), binned once on a 2-D grid of `cell` metres.
@@ -265,8 +280,11 @@ int64_t lrc_launch_count(const lrc_ctx* ctx);
  * chunks (*h_launches = number of chunks = k_trace launches).  Requires lrc_set_option(ctx, "kernel_timing", 1)
  * before the scan; synchronises on the recorded events.  This is what bench.py's roofline divides by. */
 int lrc_kernel_times(lrc_ctx* ctx, double* h_trace_ms, double* h_compact_ms, int32_t* h_launches);
-/* Tuning knobs: "variant" (traversal loop shape), "chunk_rays", "gather_chunks", "kernel_timing".
+/* Tuning knobs: "variant" (traversal loop shape), "block", "chunk_rays", "gather_chunks", "push_blocks",
+ * "kernel_timing", "l2_persist" (percent of the device's maximum persisting-L2 set-aside reserved for an access-policy
+ * window over the BVH records on every k_trace launch; 0 = off), "l2_reset" (demote all persisting lines now).
  * Unknown keys -> LRC_ERR_INVALID. */
+int lrc_default_l2_persist(void);
 int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value);
 
 #ifdef __cplusplus

@@ -17,7 +17,7 @@ from .core import (Context, NoiseConfig, ScanResult, TriangleMesh, get_context, 
 from .lidar import (DualAxisLidar, DualAxisLidarIntrinsics, Indoor8LineLidarIntrinsics, IndoorLidar, LidarIntrinsics,
                     create_lidar, get_lidar_type)
 from .raycast_engine import RaycastEngineBase, RaycastEngineGPU
-from .post import (ScanQuality, SimulationStats, frame_statistics, read_labeled_ply, scan_quality, simulation_stats,
+from .post import (LabelTransfer, ScanQuality, SimulationStats, frame_statistics, read_labeled_ply, scan_quality, simulation_stats,
                    write_labeled_ply)
 from .trajectory import AutoTrajectoryGenerator, TrajectoryQuality, Waypoint, poses_from_waypoints, shard_range
 
@@ -26,7 +26,7 @@ __version__ = "0.1.0"
 __all__ = [
     "lidar", "post", "raycast_engine", "synthetic", "trajectory",
     "ScanQuality", "SimulationStats", "frame_statistics", "scan_quality", "simulation_stats", "write_labeled_ply",
-    "read_labeled_ply",
+    "read_labeled_ply", "LabelTransfer",
     "Context", "NoiseConfig", "ScanResult", "TriangleMesh", "get_context", "mesh_arrays", "pack_labels",
     "unpack_labels", "rays_per_frame",
     "LidarIntrinsics", "Indoor8LineLidarIntrinsics", "DualAxisLidarIntrinsics", "IndoorLidar", "DualAxisLidar",

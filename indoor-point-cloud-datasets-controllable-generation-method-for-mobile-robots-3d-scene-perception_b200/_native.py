@@ -96,6 +96,8 @@ SYMBOLS = {
     "lrc_gen_rays_dual_axis": (_i32, [_vp, _vp, _i64, C.POINTER(DualAxis), C.POINTER(Noise), _vp, _vp, _vp]),
     "lrc_frame_statistics": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "lrc_pack_ply_records": (_i32, [_vp, _vp, _vp, _vp, _vp, C.c_uint32, _i64, _vp, _vp]),
+    "lrc_nn_index_build": (_i32, [_vp, _vp, _i64, _dbl, _vp]),
+    "lrc_nn_query": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lrc_collision_index_build": (_i32, [_vp, _vp, _i64, _dbl, _vp]),
     "lrc_collision_query": (_i32, [_vp, _vp, _i64, _dbl, C.POINTER(_dbl), _vp, _vp]),
     "lrc_grid_connectivity": (_i32, [_vp, _vp, C.c_int32, _vp, C.c_int32, _vp, _dbl, C.c_int32, _vp, _vp, _vp, _i64, C.POINTER(_i64), _vp]),
@@ -104,6 +106,7 @@ SYMBOLS = {
     "lrc_counters": (_i32, [_vp, C.POINTER(Counters), _i32, _vp]),
     "lrc_launch_count": (_i64, [_vp]),
     "lrc_set_option": (_i32, [_vp, C.c_char_p, _i64]),
+    "lrc_default_l2_persist": (_i32, []),
     "lrc_kernel_times": (_i32, [_vp, C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(C.c_int32)]),
 }
 

@@ -237,6 +237,10 @@ class Context:
     def set_option(self, key: str, value: int) -> None:
         nat.check(self._h, self._lib.lrc_set_option(self._h, key.encode(), int(value)))
 
+    def default_l2_persist(self) -> int:
+        """The library's default for option ``l2_persist`` (percent of the maximum persisting-L2 set-aside)."""
+        return int(self._lib.lrc_default_l2_persist())
+
     def kernel_times(self) -> dict:
         """Device time (ms) of k_trace and of the compaction kernels of the last scan (option ``kernel_timing``)."""
         tr, cp, n = C.c_double(0), C.c_double(0), C.c_int32(0)

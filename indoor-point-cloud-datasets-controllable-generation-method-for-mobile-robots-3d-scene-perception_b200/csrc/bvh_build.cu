@@ -399,17 +399,14 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
         return LRC_OK;
     }
     const int64_t n_nodes = T > 1 ? T - 1 : 1;
-    if ((size_t)(n_nodes * 4) > ctx->nodes_cap) {
-        if (ctx->nodes) LRC_CUDA(ctx, cudaFree(ctx->nodes));
-        ctx->nodes = nullptr; ctx->nodes_cap = 0;
-        LRC_CUDA(ctx, cudaMalloc((void**)&ctx->nodes, sizeof(float4) * 4 * n_nodes));
-        ctx->nodes_cap = (size_t)(n_nodes * 4);
-    }
-    if ((size_t)(T * 3) > ctx->tris_cap) {
-        if (ctx->tris) LRC_CUDA(ctx, cudaFree(ctx->tris));
-        ctx->tris = nullptr; ctx->tris_cap = 0;
-        LRC_CUDA(ctx, cudaMalloc((void**)&ctx->tris, sizeof(float4) * 3 * T));
-        ctx->tris_cap = (size_t)(T * 3);
+    {
+        const size_t nodes_bytes = align_up(sizeof(float4) * 4 * (size_t)n_nodes, 256);
+        const size_t tris_bytes = align_up(sizeof(float4) * 3 * (size_t)T, 256);
+        int rcb = lrc_grow(ctx, &ctx->bvh_block, &ctx->bvh_block_bytes, nodes_bytes + tris_bytes);
+        if (rcb) return rcb;
+        ctx->nodes = (float4*)ctx->bvh_block;
+        ctx->tris = (float4*)((char*)ctx->bvh_block + nodes_bytes);
+        ctx->bvh_bytes = nodes_bytes + tris_bytes;
     }
     if ((size_t)T > ctx->labels_cap) {
         if (ctx->labels) LRC_CUDA(ctx, cudaFree(ctx->labels));

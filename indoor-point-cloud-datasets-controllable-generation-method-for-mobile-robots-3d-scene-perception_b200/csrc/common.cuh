@@ -26,7 +26,14 @@ struct lrc_ctx {
     float4* nodes = nullptr;      // num_nodes x 4 float4 (64 B records)
     float4* tris = nullptr;       // T x 3 float4 (48 B records, Morton order): (v0|orig id) (e1|0) (e2|0)
     uint32_t* labels = nullptr;   // T, original triangle order
-    size_t nodes_cap = 0, tris_cap = 0, labels_cap = 0;   // in elements
+    void* bvh_block = nullptr;    // one allocation [nodes | tris]: a single L2 access-policy window covers both
+    size_t bvh_block_bytes = 0;
+    size_t labels_cap = 0;        // in elements
+    // L2 persistence for the BVH records (option "l2_persist"): k_trace is launched with an access-policy window over
+    // bvh_block so that streaming traffic (scratch, outputs, peers' incoming stores) cannot evict the tree
+    size_t l2_persist_max = 0, l2_window_max = 0, l2_size = 0;
+    int64_t opt_l2_persist = 0;
+    size_t bvh_bytes = 0;         // bytes of bvh_block in use
     lrc_bvh_info info = {};
     double root_area = 0.0;
 
@@ -71,6 +78,15 @@ struct lrc_ctx {
     void* ci_sorted = nullptr; size_t ci_sorted_bytes = 0;
     double ci_ox = 0, ci_oy = 0, ci_cell = 0;
     int ci_nbx = 0, ci_nby = 0;
+
+    // ---- 1-NN label transfer (nn.cu): binned annotated points ----
+    bool nn_ready = false;
+    int64_t nn_n = 0;
+    void* nn_meta = nullptr; size_t nn_meta_bytes = 0;
+    void* nn_start = nullptr; size_t nn_start_bytes = 0;
+    void* nn_sorted = nullptr; size_t nn_sorted_bytes = 0;
+    double nn_o[3] = {0, 0, 0}, nn_cell = 0;
+    int nn_nb[3] = {0, 0, 0};
 
     // ---- post-processing (post.cu) ----
     void* post_scratch = nullptr;

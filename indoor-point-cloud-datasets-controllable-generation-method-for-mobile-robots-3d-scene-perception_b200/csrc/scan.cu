@@ -438,9 +438,9 @@ __device__ __forceinline__ void push_words(const uint32_t* __restrict__ src, uin
     int64_t i = tid;
     for (; i + 3 * nthreads < nvec; i += 4 * nthreads) {            // four vectors in flight per thread
         const uint4 a = __ldcg(s4 + i), b = __ldcg(s4 + i + nthreads), c = __ldcg(s4 + i + 2 * nthreads), d = __ldcg(s4 + i + 3 * nthreads);
-        d4[i] = a; d4[i + nthreads] = b; d4[i + 2 * nthreads] = c; d4[i + 3 * nthreads] = d;
+        __stcs(d4 + i, a); __stcs(d4 + i + nthreads, b); __stcs(d4 + i + 2 * nthreads, c); __stcs(d4 + i + 3 * nthreads, d);
     }
-    for (; i < nvec; i += nthreads) d4[i] = __ldcg(s4 + i);
+    for (; i < nvec; i += nthreads) __stcs(d4 + i, __ldcg(s4 + i));
 }
 
 constexpr int PUSH_THREADS = 256;
@@ -476,8 +476,29 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
     const int TB = DENSE ? TRACE_THREADS : (int)ctx->opt_block;
     const unsigned grid = (unsigned)((n + TB - 1) / TB);
     const int has_tris = ctx->T > 0;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3((unsigned)TB); cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    cfg.attrs = attr;
+    if (ctx->opt_l2_persist && ctx->l2_persist_max > 0 && ctx->bvh_bytes > 0) {
+        // persisting lines for the BVH records; the window may be smaller than the tree (then its head -- the nodes --
+        // is covered first) and the set-aside smaller than the window (then hitRatio picks that fraction of lines)
+        const size_t win = ctx->bvh_bytes < ctx->l2_window_max ? ctx->bvh_bytes : ctx->l2_window_max;
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = ctx->bvh_block;
+        attr[0].val.accessPolicyWindow.num_bytes = win;
+        attr[0].val.accessPolicyWindow.hitRatio = win <= ctx->l2_persist_max ? 1.0f : (float)((double)ctx->l2_persist_max / (double)win);
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+        cfg.numAttrs = 1;
+    }
+    const float4* nodes = ctx->nodes;
+    const float4* tris = ctx->tris;
+    unsigned long long* counters = ctx->d_counters;
+    cudaError_t le = cudaSuccess;
 #define LRC_LAUNCH_TRACE(COUNT, VARIANT) \
-    k_trace<MODE, COUNT, DENSE, VARIANT><<<grid, TB, 0, stream>>>(g, fm, ctx->nodes, ctx->tris, n, has_tris, hp, inc, block_count, t_hit, prim, ctx->d_counters)
+    le = cudaLaunchKernelEx(&cfg, k_trace<MODE, COUNT, DENSE, VARIANT>, g, fm, nodes, tris, n, has_tris, hp, inc, block_count, t_hit, prim, counters)
     if (ctx->counting) {
         switch (ctx->opt_variant) {
             case 0: LRC_LAUNCH_TRACE(true, 0); break;
@@ -494,6 +515,7 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
         }
     }
 #undef LRC_LAUNCH_TRACE
+    if (le != cudaSuccess) return lrc_fail(ctx, LRC_ERR_CUDA, "launch k_trace: %s", cudaGetErrorString(le));
     LRC_CHECK_LAUNCH(ctx, "k_trace");
     return LRC_OK;
 }
@@ -694,6 +716,9 @@ int precheck(lrc_ctx* ctx, const char* who)
 // ======================================================================================================
 extern "C" int lrc_abi_version(void) { return LRC_ABI_VERSION; }
 
+#define LRC_DEFAULT_L2_PERSIST 0
+extern "C" int lrc_default_l2_persist(void) { return LRC_DEFAULT_L2_PERSIST; }
+
 extern "C" int lrc_create(int device, lrc_ctx** out)
 {
     if (!out) return lrc_fail(nullptr, LRC_ERR_INVALID, "lrc_create: out is NULL");
@@ -713,6 +738,9 @@ extern "C" int lrc_create(int device, lrc_ctx** out)
         return lrc_fail(nullptr, LRC_ERR_CUDA, "lrc_create: cudaSetDevice: %s", cudaGetErrorString(e));
     lrc_ctx* ctx = new lrc_ctx();
     ctx->device = device;
+    ctx->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+    ctx->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+    ctx->l2_size = (size_t)prop.l2CacheSize;
     *out = ctx;
     return LRC_OK;
 }
@@ -721,10 +749,11 @@ extern "C" void lrc_destroy(lrc_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->nodes); cudaFree(ctx->tris); cudaFree(ctx->labels);
+    cudaFree(ctx->bvh_block); cudaFree(ctx->labels);
     cudaFree(ctx->scratch); cudaFree(ctx->scratch2); cudaFree(ctx->tables); cudaFree(ctx->d_counters);
     cudaFree(ctx->host_dev); cudaFree(ctx->mesh_dev); cudaFree(ctx->post_scratch);
     cudaFree(ctx->ci_meta); cudaFree(ctx->ci_start); cudaFree(ctx->ci_sorted);
+    cudaFree(ctx->nn_meta); cudaFree(ctx->nn_start); cudaFree(ctx->nn_sorted);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->scratch_event) cudaEventDestroy(ctx->scratch_event);
     for (cudaEvent_t e : ctx->kt_events) cudaEventDestroy(e);
@@ -787,6 +816,20 @@ extern "C" int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value)
 {
     if (!ctx || !key) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_option: NULL argument");
     if (!strcmp(key, "chunk_rays")) { if (value < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "chunk_rays must be >= 1"); ctx->opt_chunk_rays = value; return LRC_OK; }
+    if (!strcmp(key, "l2_persist")) {
+        // value = percentage of the device's maximum persisting-L2 set-aside to reserve (0 = off)
+        if (value < 0 || value > 100) return lrc_fail(ctx, LRC_ERR_INVALID, "l2_persist must be in [0, 100]");
+        LRC_CUDA(ctx, cudaSetDevice(ctx->device));
+        cudaDeviceProp prop;
+        LRC_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+        const size_t want = (size_t)((double)prop.persistingL2CacheMaxSize * (double)value / 100.0);
+        LRC_CUDA(ctx, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+        if (value == 0) LRC_CUDA(ctx, cudaCtxResetPersistingL2Cache());
+        ctx->l2_persist_max = want;
+        ctx->opt_l2_persist = value;
+        return LRC_OK;
+    }
+    if (!strcmp(key, "l2_reset")) { LRC_CUDA(ctx, cudaSetDevice(ctx->device)); LRC_CUDA(ctx, cudaCtxResetPersistingL2Cache()); return LRC_OK; }
     if (!strcmp(key, "push_blocks")) { if (value < 1 || value > 1024) return lrc_fail(ctx, LRC_ERR_INVALID, "push_blocks must be in [1, 1024]"); ctx->opt_push_blocks = value; return LRC_OK; }
     if (!strcmp(key, "gather_chunks")) { if (value < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "gather_chunks must be >= 1"); ctx->opt_gather_chunks = value; return LRC_OK; }
     if (!strcmp(key, "block")) {

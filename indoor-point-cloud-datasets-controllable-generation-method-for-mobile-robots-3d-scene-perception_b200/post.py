@@ -145,6 +145,72 @@ def write_labeled_ply(ctx: Context, path, result: ScanResult, tri_rgb=None, defa
     return len(hdr) + int(host.numel())
 
 
+class LabelTransfer:
+    """Exact 1-nearest-neighbour transfer of colours / semantic / instance labels from annotated points to hit points --
+    what ``S3DISSimScene._get_colors_and_labels_from_s3dis`` does per frame with a scikit-learn ball tree
+    (reference containers/s3dis_sim_scene.py:413-424), here on the GPU (``lrc_nn_index_build`` / ``lrc_nn_query``).
+
+    ``points``: (n,3) annotated points (float64, as loaded from the S3DIS annotation files); ``colors``: (n,3) floats
+    in [0,1] (reference convention, :483 turns them into bytes with ``(c * 255).astype(uint8)``) or uint8;
+    ``semantic`` / ``instance``: (n,) integer labels.  Indices agree with the ball tree bit for bit except at exact
+    distance ties (smaller index here)."""
+
+    def __init__(self, ctx: Context, points, colors=None, semantic=None, instance=None, cell: float = 0.0):
+        self.ctx = ctx
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        self.n = len(pts)
+        dev = ctx.device
+        with torch.cuda.device(dev):
+            self._pts = torch.from_numpy(pts).to(dev)
+            nat.check(ctx._h, ctx._lib.lrc_nn_index_build(ctx._h, _ptr(self._pts), self.n, float(cell), ctx._stream()))
+        self._lab = self._rgb = None
+        if semantic is not None or instance is not None:
+            sem = np.zeros(self.n, np.uint32) if semantic is None else np.asarray(semantic).astype(np.uint32)
+            ins = np.zeros(self.n, np.uint32) if instance is None else np.asarray(instance).astype(np.uint32)
+            lab = (sem & 0xFFFF) | ((ins & 0xFFFF) << 16)
+            self._lab = torch.from_numpy(lab.view(np.int32)).to(dev)
+        if colors is not None:
+            c = np.asarray(colors)
+            if c.dtype != np.uint8:
+                c = (c * 255).astype(np.uint8)                   # reference :483
+            self._rgb = torch.from_numpy(pack_rgb(c).view(np.int32)).to(dev)
+
+    def query(self, points, want_distance: bool = False) -> Dict[str, torch.Tensor]:
+        """points: (M,3) float32 (device tensor or ndarray).  -> device tensors: index int32, label / rgb int32 holding
+        uint32 bits (present when the tables were given), distance float64 (optional)."""
+        ctx = self.ctx
+        with torch.cuda.device(ctx.device):
+            q = points if isinstance(points, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(points, dtype=np.float32))
+            q = q.to(device=ctx.device, dtype=torch.float32).contiguous().reshape(-1, 3)
+            M = q.shape[0]
+            idx = torch.empty(max(M, 1), dtype=torch.int32, device=ctx.device)[:M]
+            dist = torch.empty(max(M, 1), dtype=torch.float64, device=ctx.device)[:M] if want_distance else None
+            lab = torch.empty(max(M, 1), dtype=torch.int32, device=ctx.device)[:M] if self._lab is not None else None
+            rgb = torch.empty(max(M, 1), dtype=torch.int32, device=ctx.device)[:M] if self._rgb is not None else None
+            nat.check(ctx._h, ctx._lib.lrc_nn_query(ctx._h, _ptr(q), M, _ptr(idx), _ptr(dist), _ptr(self._lab), _ptr(lab),
+                                                    _ptr(self._rgb), _ptr(rgb), ctx._stream()))
+        out = {"index": idx}
+        if lab is not None:
+            out["label"] = lab
+        if rgb is not None:
+            out["rgb"] = rgb
+        if dist is not None:
+            out["distance"] = dist
+        return out
+
+    def relabel(self, result: ScanResult) -> ScanResult:
+        """A copy of ``result`` whose ``label`` comes from the annotated points and whose ``prim_id`` holds the index
+        of the nearest annotated point (so ``write_labeled_ply(..., tri_rgb=self.rgb_table)`` colours by neighbour)."""
+        r = self.query(result.points)
+        return ScanResult(points=result.points, incident=result.incident, prim_id=r["index"],
+                          label=r.get("label", result.label), ray_idx=result.ray_idx, frame_offset=result.frame_offset,
+                          frame_offset_host=result.frame_offset_host)
+
+    @property
+    def rgb_table(self) -> Optional[torch.Tensor]:
+        return self._rgb
+
+
 def read_labeled_ply(path) -> Dict[str, np.ndarray]:
     """Parse the 8-attribute binary PLY the way the reference's consumer does (lidar_net_bbox_visualizer.py:72-126:
     header lines until ``end_header``, vertex count from ``element vertex``, 12 + 3 bytes skipped, ``HH`` labels)."""

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--variants", default="0,1,2,3")
     ap.add_argument("--blocks", default="32,64,128")
+    ap.add_argument("--l2", default="0", help="comma list of l2_persist percentages")
     args = ap.parse_args()
     w, mesh, poses, intr = bench.make_workload(lrc, args.workload, 1)
     dev = torch.device("cuda", 0)
@@ -39,12 +40,15 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     ref = None
     ctx.set_option("kernel_timing", 1)
-    for var in [int(x) for x in args.variants.split(",")]:
+    import itertools
+    for var, l2 in itertools.product([int(x) for x in args.variants.split(",")], [int(x) for x in args.l2.split(",")]):
         for blk in [int(x) for x in args.blocks.split(",")]:
             ctx.set_option("variant", var)
             ctx.set_option("block", blk)
+            ctx.set_option("l2_persist", l2)
             tr, cp = [], []
             for r in range(args.reps + 2):
+                ctx.set_option("l2_reset", 1)
                 flush.fill_(r & 255)
                 ctx.scan_enqueue(poses_d, intr, noise, bufs)
                 torch.cuda.synchronize()
@@ -56,7 +60,7 @@ def main():
             sig = (m, int(bufs["prim"][:m].to(torch.int64).sum().item()), float(bufs["xyz"][:m].double().sum().item()))
             if ref is None:
                 ref = sig
-            print(json.dumps({"variant": var, "block": blk, "trace_ms": round(float(np.mean(tr)), 4),
+            print(json.dumps({"variant": var, "block": blk, "l2_persist": l2, "trace_ms": round(float(np.mean(tr)), 4),
                               "trace_ms_min": round(float(np.min(tr)), 4), "compact_ms": round(float(np.mean(cp)), 4),
                               "Mrays_s_trace": round(P * n_frame / np.mean(tr) / 1e3, 1), "same_output": sig == ref}), flush=True)
 
