@@ -322,6 +322,8 @@ def run_ours(args):
         ctx.set_option("gather_chunks", args.gather_chunks)
         if args.push_blocks:
             ctx.set_option("push_blocks", args.push_blocks)
+        if args.gather_ramp:
+            ctx.set_option("gather_ramp", args.gather_ramp)
         peer.enable()
 
     def one_step():
@@ -498,6 +500,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N>1: how the clouds are exchanged")
     ap.add_argument("--gather-chunks", type=int, default=4, help="N>1: pose chunks per rank for the overlapped all-gather")
+    ap.add_argument("--gather-ramp", type=int, default=None, help="N>1: first chunk = regular chunk / ramp")
     ap.add_argument("--push-blocks", type=int, default=None, help="N>1: blocks per target of the exchange kernel")
     ap.add_argument("--e2e-chunk", type=int, default=None, help="poses per chunk of the pipelined e2e path")
     ap.add_argument("--l2-persist", type=int, default=None, help="percent of the max persisting-L2 set-aside reserved for the BVH window (0 = off)")

@@ -68,6 +68,7 @@ struct lrc_ctx {
         int64_t point_base = 0, frame_base = 0, capacity = 0;
     } gather;
     int64_t opt_gather_chunks = 4;
+    int64_t opt_gather_ramp = 1;        // first gather chunk = regular chunk / ramp
     int64_t opt_push_blocks = 16;       // blocks per target of the k_push exchange kernel
 
     // ---- planner support (plan.cu): binned vertex index ----

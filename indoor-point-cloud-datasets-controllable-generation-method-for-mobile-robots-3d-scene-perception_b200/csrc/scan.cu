@@ -553,7 +553,14 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
         const int64_t want = (P + ctx->opt_gather_chunks - 1) / ctx->opt_gather_chunks;
         if (want >= 1 && want < frames_per_chunk) frames_per_chunk = want;
     }
-    const int64_t n_chunks = (P + frames_per_chunk - 1) / frames_per_chunk;
+    // With gather targets the exchange, not the traversal, is the long pole at 4+ GPUs (NVLink ingress): start it early
+    // with a short first chunk ("gather_ramp" = its size as a fraction 1/ramp of a regular chunk; 1 = uniform chunks).
+    int64_t first_chunk = frames_per_chunk;
+    if (gather && MODE != MODE_RAYS && ctx->opt_gather_ramp > 1 && P > frames_per_chunk) {
+        first_chunk = frames_per_chunk / ctx->opt_gather_ramp;
+        if (first_chunk < 1) first_chunk = 1;
+    }
+    const int64_t n_chunks = 1 + (P > first_chunk ? (P - first_chunk + frames_per_chunk - 1) / frames_per_chunk : 0);
     const bool piped = n_chunks > 1;
     const int n_slots = piped ? 2 : 1;
     const int64_t chunk_rays = frames_per_chunk * N;
@@ -606,8 +613,9 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
     }
     for (int64_t c = 0; c < n_chunks; ++c) {
         const int slot = piped ? (int)(c & 1) : 0;
-        const int64_t f0 = c * frames_per_chunk;
-        const int64_t nf = (f0 + frames_per_chunk <= P) ? frames_per_chunk : P - f0;
+        const int64_t f0 = c == 0 ? 0 : first_chunk + (c - 1) * frames_per_chunk;
+        const int64_t want_nf = c == 0 ? first_chunk : frames_per_chunk;
+        const int64_t nf = (f0 + want_nf <= P) ? want_nf : P - f0;
         const int64_t n = nf * N;
         const int64_t nb = (n + TB - 1) / TB;
         float4* hp = (float4*)((char*)ctx->scratch + slot_bytes * slot);
@@ -830,6 +838,7 @@ extern "C" int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value)
         return LRC_OK;
     }
     if (!strcmp(key, "l2_reset")) { LRC_CUDA(ctx, cudaSetDevice(ctx->device)); LRC_CUDA(ctx, cudaCtxResetPersistingL2Cache()); return LRC_OK; }
+    if (!strcmp(key, "gather_ramp")) { if (value < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "gather_ramp must be >= 1"); ctx->opt_gather_ramp = value; return LRC_OK; }
     if (!strcmp(key, "push_blocks")) { if (value < 1 || value > 1024) return lrc_fail(ctx, LRC_ERR_INVALID, "push_blocks must be in [1, 1024]"); ctx->opt_push_blocks = value; return LRC_OK; }
     if (!strcmp(key, "gather_chunks")) { if (value < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "gather_chunks must be >= 1"); ctx->opt_gather_chunks = value; return LRC_OK; }
     if (!strcmp(key, "block")) {

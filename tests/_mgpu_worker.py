@@ -47,15 +47,21 @@ def main():
     pg = PeerGather(engine.ctx, cap_per_rank=6 * 64000, frames_per_rank=6)
     pg.enable()
     engine.ctx.set_option("gather_chunks", 3)
-    try:
+    for ramp, blocks in ((1, 16), (2, 3)):          # uniform chunks, then a short first chunk and few exchange blocks
+        engine.ctx.set_option("gather_ramp", ramp)
+        engine.ctx.set_option("push_blocks", blocks)
+        pg.buffer.zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
         for _ in range(2):
             local = engine.simulate(poses12[sl.start:sl.stop], intr, noise=local_noise).numpy()
         pg.synchronize()
         got = pg.assemble_numpy()
-    finally:
-        pg.disable()
-    assert np.array_equal(got["frame_offset"], ref["frame_offset"])
-    assert np.array_equal(got["points"], ref["points"]) and np.array_equal(got["label"], ref["label"])
+        assert np.array_equal(got["frame_offset"], ref["frame_offset"]), ramp
+        assert np.array_equal(got["points"], ref["points"]) and np.array_equal(got["label"], ref["label"]), ramp
+        dist.barrier()
+    pg.disable()
+    engine.ctx.set_option("gather_ramp", 1)
     a, b = ref["frame_offset"][sl.start], ref["frame_offset"][sl.stop]
     assert np.array_equal(local["points"], ref["points"][a:b]) and np.array_equal(local["incident"], ref["incident"][a:b])
     pg.close()
