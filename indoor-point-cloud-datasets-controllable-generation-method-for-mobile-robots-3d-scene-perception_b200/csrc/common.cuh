@@ -106,7 +106,7 @@ struct lrc_ctx {
     // ---- options ----
     int64_t opt_block = 128;            // threads per traversal block
     int64_t opt_chunk_rays = 1 << 26;   // rays per traversal/epilogue chunk (bounds scratch: 16 B per ray)
-    int64_t opt_variant = 1;            // traversal kernel variant (1 = while-while)
+    int64_t opt_variant = 5;            // traversal kernel variant: while-while loop, 32-register cap (64 warps per SM)
 };
 
 extern char g_lrc_global_err[512];

@@ -172,7 +172,7 @@ constexpr int TRACE_THREADS = 128;
 // (float4; id = MISS when the ray missed, was dropped or failed the range test), the incident angle, and per BLOCK
 // the number of kept rays (block_count) -- the first stage of the ordered compaction.
 template <int MODE, bool COUNT, bool OUT_DENSE, int VARIANT>
-__global__ void __launch_bounds__(TRACE_THREADS)
+__global__ void __launch_bounds__(TRACE_THREADS, (VARIANT & 4) ? 16 : 1)   // VARIANT bit 2: cap registers at 32 for 64 warps per SM
 k_trace(RayGen g, FrameMath fm, const float4* __restrict__ nodes, const float4* __restrict__ tris, int64_t n, int has_tris,
         float4* __restrict__ hp, double* __restrict__ inc_out, unsigned* __restrict__ block_count, float* __restrict__ t_hit,
         uint32_t* __restrict__ prim_id, unsigned long long* counters)
@@ -504,6 +504,7 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
             case 0: LRC_LAUNCH_TRACE(true, 0); break;
             case 1: LRC_LAUNCH_TRACE(true, 1); break;
             case 2: LRC_LAUNCH_TRACE(true, 2); break;
+            case 5: LRC_LAUNCH_TRACE(true, 5); break;
             default: LRC_LAUNCH_TRACE(true, 3); break;
         }
     } else {
@@ -511,6 +512,7 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
             case 0: LRC_LAUNCH_TRACE(false, 0); break;
             case 1: LRC_LAUNCH_TRACE(false, 1); break;
             case 2: LRC_LAUNCH_TRACE(false, 2); break;
+            case 5: LRC_LAUNCH_TRACE(false, 5); break;
             default: LRC_LAUNCH_TRACE(false, 3); break;
         }
     }
@@ -645,6 +647,9 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
         if (gather && !q.out.label && ctx->T > 0) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_gather: the scan's lrc_out needs a label array");
         k_compact<<<(unsigned)nb, TB, 0, aux>>>(q);
         LRC_CHECK_LAUNCH(ctx, "k_compact");
+        // the scratch slot is free as soon as the compaction has read it: the traversal of chunk c+2 must not wait for
+        // the exchange of chunk c
+        if (piped) LRC_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[slot], aux));
         if (gather) {
             PushParams pp;
             pp.xyz = out->xyz; pp.label = q.out.label; pp.frame_offset = out->frame_offset; pp.run = run + c;
@@ -653,7 +658,10 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
             LRC_CHECK_LAUNCH(ctx, "k_push");
         }
         if (timing) { LRC_CUDA(ctx, cudaEventRecord(ctx->kt_events[4 * c + 3], aux)); ctx->kt_used = (size_t)(4 * (c + 1)); }
-        if (piped) LRC_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[slot], aux));
+    }
+    if (gather && piped) {   // the last exchange kernel on the auxiliary stream
+        LRC_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[2], aux));
+        LRC_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->pipe_ev[2], 0));
     }
     if (piped) {   // the caller's stream owns the result: join the auxiliary stream back
         const int last_slot = (int)((n_chunks - 1) & 1);
@@ -848,7 +856,7 @@ extern "C" int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value)
     }
     if (!strcmp(key, "kernel_timing")) { ctx->opt_kernel_timing = value != 0; ctx->kt_used = 0; return LRC_OK; }
     if (!strcmp(key, "variant")) {
-        if (value < 0 || value > 3) return lrc_fail(ctx, LRC_ERR_INVALID, "variant must be 0..3");
+        if (value < 0 || (value > 3 && value != 5)) return lrc_fail(ctx, LRC_ERR_INVALID, "variant must be 0..3 or 5");
         ctx->opt_variant = value;
         return LRC_OK;
     }

@@ -144,7 +144,7 @@ __device__ __forceinline__ int inner_step(const float4* __restrict__ nodes, int 
 
 // Stack-based closest-hit traversal.  VARIANT bit 0: 0 = one node (inner or leaf) per loop trip ("if-if"),
 // 1 = "while-while" -- run down inner nodes until a leaf (or the end) is reached, then test the leaf.
-// VARIANT bit 1: node records fetched with 256-bit loads.
+// VARIANT bit 1: node records fetched with 256-bit loads.  VARIANT bit 2 (scan.cu): 32-register cap (64 warps per SM).
 template <int VARIANT, bool COUNT>
 __device__ __forceinline__ void trace_ray(const float4* __restrict__ nodes, const float4* __restrict__ tris, float ox,
                                           float oy, float oz, float dx, float dy, float dz, float& best_t,

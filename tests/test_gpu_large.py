@@ -64,3 +64,66 @@ def test_c2_full_trajectory_properties(engine, lrc, office, office_poses):
     for k in ("points", "incident", "prim_id", "label", "ray_idx"):
         assert np.array_equal(np.concatenate([a[k], b[k]]), out[k]), k
     assert np.array_equal(np.concatenate([a["frame_offset"], a["frame_offset"][-1] + b["frame_offset"][1:]]), off)
+
+
+def test_c3_blk2go_noise_labels_subset_vs_oracle(engine, lrc, orc, office, office_poses):
+    """BASELINE config 3 (dual-axis BLK2GO, angle noise + dropout + labels, 1M triangles): 2 poses against the oracle's
+    identical Philox stream; dropped rays never reach the output, labels follow triangle ids."""
+    intr = lrc.DualAxisLidarIntrinsics.create_blk2go_dual_axis()
+    noise = lrc.NoiseConfig.from_intrinsics(intr, seed=2, pose_index_base=40)
+    sel = office_poses[[40, 41]]
+    res = engine.simulate(sel, intr, office, noise=noise).numpy()
+    scene = orc.OracleScene((office.vertices, office.triangles))
+    n_bad = n_all = 0
+    for k in range(2):
+        rays, keep = orc.gen_rays_dual_axis(sel[k], orc.dual_params(intr), seed=2, pose_idx=40 + k, compact=False)
+        kept = np.nonzero(keep)[0]
+        assert 0.97 * 64000 < len(kept) < 0.99 * 64000                    # ~2 % dropout
+        t, pid = scene.cast_rays(rays[kept])
+        fr = orc.epilogue_c(rays[kept], t, pid, center=sel[k][:3, 3], max_range=intr.max_range, tri_label=office.triangle_labels)
+        a, b = res["frame_offset"][k], res["frame_offset"][k + 1]
+        assert b - a == len(fr.points)
+        assert np.array_equal(res["ray_idx"][a:b], kept[fr.ray_idx])       # indices are positions in the DENSE table
+        same = res["prim_id"][a:b] == fr.prim_id
+        n_bad += int((~same).sum())
+        n_all += len(same)
+        assert np.array_equal(res["points"][a:b][same], fr.points[same])
+        assert np.array_equal(res["label"][a:b], office.triangle_labels[res["prim_id"][a:b]])
+    assert n_bad / n_all <= 1e-5
+
+
+def test_c4_floor_chunking_and_host_path_properties(engine, lrc):
+    """BASELINE config 4's mesh (multi-room floor, 5M triangles): the BVH does not fit L2.  Size-independent
+    properties: tiny scratch chunks (forces the pipelined multi-chunk path), the host-buffer path and the one-launch
+    path produce identical bits; re-running is idempotent; frames are ray-ordered and labelled by triangle."""
+    mesh = lrc.synthetic.floor_plan(target_tris=5_000_000, seed=0)
+    poses = lrc.poses_from_waypoints(lrc.synthetic.floor_plan_waypoints(24))
+    intr = lrc.DualAxisLidarIntrinsics.create_blk2go_dual_axis()
+    noise = lrc.NoiseConfig.from_intrinsics(intr, seed=9)
+    ref = engine.simulate(poses, intr, mesh, noise=noise).numpy()
+    info = engine.ctx.bvh_info()
+    assert 4_900_000 <= info["num_tris"] <= 5_100_000 and info["max_depth"] < 64
+    assert info["bytes_nodes"] + info["bytes_tris"] > 4 * 126e6
+    again = engine.simulate(poses, intr, noise=noise).numpy()
+    engine.ctx.set_option("chunk_rays", 5 * 64000)                          # 5 poses per chunk -> 5 chunks, double-buffered
+    try:
+        chunked = engine.simulate(poses, intr, noise=noise).numpy()
+    finally:
+        engine.ctx.set_option("chunk_rays", 1 << 26)
+    host = engine.simulate_to_host(poses, intr, noise=noise, chunk_poses=7)
+    for k in ("points", "incident", "prim_id", "label", "ray_idx", "frame_offset"):
+        assert np.array_equal(again[k], ref[k]), k
+        assert np.array_equal(chunked[k], ref[k]), k
+    assert np.array_equal(host["points"], ref["points"]) and np.array_equal(host["incident"], ref["incident"])
+    assert np.array_equal(host["label"], ref["label"]) and np.array_equal(host["frame_offset"], ref["frame_offset"])
+    off = ref["frame_offset"]
+    assert off[-1] > 0.9 * 24 * 64000
+    for f in (0, 11, 23):
+        r = ref["ray_idx"][off[f]:off[f + 1]].astype(np.int64)
+        assert np.all(np.diff(r) > 0)
+    assert np.array_equal(ref["label"], mesh.triangle_labels[ref["prim_id"]])
+    # a different seed changes the cloud, the same seed with a shifted pose base reproduces the tail of the trajectory
+    tail = engine.simulate(poses[12:], intr, noise=lrc.NoiseConfig.from_intrinsics(intr, seed=9, pose_index_base=12)).numpy()
+    assert np.array_equal(tail["points"], ref["points"][off[12]:])
+    other = engine.simulate(poses[:2], intr, noise=lrc.NoiseConfig.from_intrinsics(intr, seed=10)).numpy()
+    assert not np.array_equal(other["frame_offset"], ref["frame_offset"][:3]) or not np.array_equal(other["points"], ref["points"][:off[2]])
