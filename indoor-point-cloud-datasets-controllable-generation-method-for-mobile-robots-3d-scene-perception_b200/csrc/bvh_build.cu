@@ -364,6 +364,29 @@ __global__ void k_single_leaf_root(const float4* leaf_lo, const float4* leaf_hi,
     meta->root_hi[0] = h.x; meta->root_hi[1] = h.y; meta->root_hi[2] = h.z;
 }
 
+// Heap-ordered copy of the top K node records (entry h: children at 2h+1, 2h+2) for the traversal variant that stages
+// the top of the tree in shared memory.  One block; levels are resolved one after the other.
+__global__ void __launch_bounds__(256) k_top_table(const float4* __restrict__ nodes, float4* __restrict__ top, int K)
+{
+    __shared__ int gid[256];
+    for (int h = threadIdx.x; h < 256; h += blockDim.x) gid[h] = h == 0 ? 0 : -1;
+    __syncthreads();
+    for (int s = 1; s < K; s = 2 * s + 1) {                 // level [s, 2s+1)
+        for (int h = s + threadIdx.x; h < min(2 * s + 1, K); h += blockDim.x) {
+            const int p = (h - 1) >> 1;
+            if (gid[p] >= 0) {
+                const float4 n3 = nodes[4 * (int64_t)gid[p] + 3];
+                const int link = __float_as_int((h & 1) ? n3.x : n3.y);
+                gid[h] = link >= 0 ? link : -1;             // a leaf child has no record
+            }
+        }
+        __syncthreads();
+    }
+    for (int h = threadIdx.x; h < K; h += blockDim.x)
+        for (int k = 0; k < 4; ++k)
+            top[4 * h + k] = gid[h] >= 0 ? nodes[4 * (int64_t)gid[h] + k] : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // SAH diagnostic: sum of the surface areas of every child box stored in the node records
 __global__ void k_sah_sum(const float4* __restrict__ nodes, int64_t n_nodes, double* out)
 {
@@ -499,6 +522,12 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
         k_refit<<<gT, TB, 0, stream>>>((int)T, parent_leaf, parent_node, children, leaf_lo, leaf_hi, node_lo, node_hi, flags,
                                        ctx->nodes, meta);
         LRC_CHECK_LAUNCH(ctx, "k_refit");
+    }
+    {
+        const int K = (1 << LRC_TOP_LEVELS_MAX) - 1;
+        if (!ctx->top_table) LRC_CUDA(ctx, cudaMalloc((void**)&ctx->top_table, sizeof(float4) * 4 * K));
+        k_top_table<<<1, 256, 0, stream>>>(ctx->nodes, ctx->top_table, K);
+        LRC_CHECK_LAUNCH(ctx, "k_top_table");
     }
     LRC_CUDA(ctx, cudaMemcpyAsync(&hm, meta, sizeof hm, cudaMemcpyDeviceToHost, stream));
     LRC_CUDA(ctx, cudaStreamSynchronize(stream));

@@ -13,6 +13,7 @@
 #define LRC_STACK_DEPTH 64        // per-ray traversal stack entries (checked against the built tree)
 #define LRC_MAX_H 4096            // scan lines per single-axis sensor
 #define LRC_MAX_GATHER 16         // == lrc_gather's array length
+#define LRC_TOP_LEVELS_MAX 8      // top-of-tree table: 2^8 - 1 = 255 node records in heap order (16 KB)
 
 struct lrc_ctx {
     int device = 0;
@@ -26,6 +27,8 @@ struct lrc_ctx {
     float4* nodes = nullptr;      // num_nodes x 4 float4 (64 B records)
     float4* tris = nullptr;       // T x 3 float4 (48 B records, Morton order): (v0|orig id) (e1|0) (e2|0)
     uint32_t* labels = nullptr;   // T, original triangle order
+    float4* top_table = nullptr;  // (2^LRC_TOP_LEVELS_MAX - 1) x 4 float4: copies of the top nodes in heap order
+    int64_t opt_top_levels = 6;   // levels staged in shared memory by the VARIANT-bit-3 traversal kernel
     void* bvh_block = nullptr;    // one allocation [nodes | tris]: a single L2 access-policy window covers both
     size_t bvh_block_bytes = 0;
     size_t labels_cap = 0;        // in elements

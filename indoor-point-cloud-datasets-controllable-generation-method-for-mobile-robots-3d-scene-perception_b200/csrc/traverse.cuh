@@ -113,25 +113,42 @@ __device__ __forceinline__ void leaf_test(const float4* __restrict__ tris, int l
 }
 
 // One step at an inner node: returns the next link (child to descend into, or a popped entry, or the sentinel).
-template <bool COUNT, bool WIDE>
-__device__ __forceinline__ int inner_step(const float4* __restrict__ nodes, int cur, const RaySlab& s, float best_t,
-                                          int* stack, int& sp, unsigned& n_nodes)
+// Top of the tree staged in shared memory (VARIANT bit 3): `s_top` holds the first top_n node records in HEAP order
+// (entry h has its children at 2h+1 / 2h+2), copied there by every block; a link >= LRC_TOP_BASE addresses that table.
+// Records are unmodified copies, so a child link is redirected into the table on the fly when its heap slot exists.
+#define LRC_TOP_BASE 0x40000000   // node ids are < 2^30 (lrc_set_mesh)
+
+template <bool COUNT, bool WIDE, bool TOP>
+__device__ __forceinline__ int inner_step(const float4* __restrict__ nodes, const float4* s_top, int top_n, int cur,
+                                          const RaySlab& s, float best_t, int* stack, int& sp, unsigned& n_nodes)
 {
-    const float4* np = nodes + 4 * (int64_t)cur;
     float4 n0, n1, n2;
-    float2 n3;
-    if (WIDE) {
-        const F8 lo = ldg256(np), hi = ldg256(np + 2);
-        n0 = lo.a; n1 = lo.b; n2 = hi.a; n3 = make_float2(hi.b.x, hi.b.y);
+    int l0, l1;
+    if (TOP && cur >= LRC_TOP_BASE) {
+        const int h = cur - LRC_TOP_BASE;
+        const float4* np = s_top + 4 * h;
+        n0 = np[0]; n1 = np[1]; n2 = np[2];
+        const float2 n3 = *reinterpret_cast<const float2*>(np + 3);
+        l0 = __float_as_int(n3.x); l1 = __float_as_int(n3.y);
+        const int c0 = 2 * h + 1;
+        if (l0 >= 0 && c0 < top_n) l0 = LRC_TOP_BASE + c0;
+        if (l1 >= 0 && c0 + 1 < top_n) l1 = LRC_TOP_BASE + c0 + 1;
     } else {
-        n0 = __ldg(np + 0); n1 = __ldg(np + 1); n2 = __ldg(np + 2);
-        n3 = __ldg(reinterpret_cast<const float2*>(np + 3));
+        const float4* np = nodes + 4 * (int64_t)cur;
+        float2 n3;
+        if (WIDE) {
+            const F8 lo = ldg256(np), hi = ldg256(np + 2);
+            n0 = lo.a; n1 = lo.b; n2 = hi.a; n3 = make_float2(hi.b.x, hi.b.y);
+        } else {
+            n0 = __ldg(np + 0); n1 = __ldg(np + 1); n2 = __ldg(np + 2);
+            n3 = __ldg(reinterpret_cast<const float2*>(np + 3));
+        }
+        l0 = __float_as_int(n3.x); l1 = __float_as_int(n3.y);
     }
     if (COUNT) ++n_nodes;
     float t0, t1;
     const bool h0 = slab_ch(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, s, best_t, t0);
     const bool h1 = slab_ch(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, s, best_t, t1);
-    const int l0 = __float_as_int(n3.x), l1 = __float_as_int(n3.y);
     if (h0 && h1) {
         const bool swp = t1 < t0;              // nearer child first, farther one on the stack
         stack[sp++] = swp ? l0 : l1;
@@ -145,8 +162,10 @@ __device__ __forceinline__ int inner_step(const float4* __restrict__ nodes, int 
 // Stack-based closest-hit traversal.  VARIANT bit 0: 0 = one node (inner or leaf) per loop trip ("if-if"),
 // 1 = "while-while" -- run down inner nodes until a leaf (or the end) is reached, then test the leaf.
 // VARIANT bit 1: node records fetched with 256-bit loads.  VARIANT bit 2 (scan.cu): 32-register cap (64 warps per SM).
+// VARIANT bit 3: the first top_n nodes (heap order) are read from shared memory.
 template <int VARIANT, bool COUNT>
-__device__ __forceinline__ void trace_ray(const float4* __restrict__ nodes, const float4* __restrict__ tris, float ox,
+__device__ __forceinline__ void trace_ray(const float4* __restrict__ nodes, const float4* __restrict__ tris,
+                                          const float4* s_top, int top_n, float ox,
                                           float oy, float oz, float dx, float dy, float dz, float& best_t,
                                           uint32_t& best_id, unsigned& n_nodes, unsigned& n_tris)
 {
@@ -155,12 +174,13 @@ __device__ __forceinline__ void trace_ray(const float4* __restrict__ nodes, cons
     const RaySlab s = make_slab(ox, oy, oz, dx, dy, dz);
     int stack[LRC_STACK_DEPTH];
     int sp = 0;
-    int cur = 0;
     constexpr bool WIDE = (VARIANT & 2) != 0;
+    constexpr bool TOP = (VARIANT & 8) != 0;
+    int cur = (TOP && top_n > 0) ? LRC_TOP_BASE : 0;
     if ((VARIANT & 1) == 0) {
         while (cur != LRC_SENTINEL) {
             if (cur >= 0) {
-                cur = inner_step<COUNT, WIDE>(nodes, cur, s, best_t, stack, sp, n_nodes);
+                cur = inner_step<COUNT, WIDE, TOP>(nodes, s_top, top_n, cur, s, best_t, stack, sp, n_nodes);
             } else {
                 if (COUNT) ++n_tris;
                 leaf_test(tris, cur, ox, oy, oz, dx, dy, dz, best_t, best_id);
@@ -169,7 +189,7 @@ __device__ __forceinline__ void trace_ray(const float4* __restrict__ nodes, cons
         }
     } else {
         while (cur != LRC_SENTINEL) {
-            while (cur >= 0) cur = inner_step<COUNT, WIDE>(nodes, cur, s, best_t, stack, sp, n_nodes);
+            while (cur >= 0) cur = inner_step<COUNT, WIDE, TOP>(nodes, s_top, top_n, cur, s, best_t, stack, sp, n_nodes);
             if (cur != LRC_SENTINEL) {
                 if (COUNT) ++n_tris;
                 leaf_test(tris, cur, ox, oy, oz, dx, dy, dz, best_t, best_id);

@@ -321,3 +321,25 @@ def test_gather_targets_and_pipelined_compaction_single_gpu(engine, lrc, c1):
     finally:
         engine.ctx.set_option("gather_chunks", 4)
         pg.close()
+
+
+def test_all_traversal_variants_and_block_sizes_give_identical_bits(engine, lrc, orc, c1):
+    """Loop shape (if-if / while-while), 256-bit node loads, the 32-register build, the shared-memory top of the tree
+    (1..8 levels, also on trees smaller than the table) and the block size are tuning knobs: none may change a bit."""
+    ctx = engine.ctx
+    poses = lrc.poses_from_waypoints([lrc.Waypoint(3.1, 2.7, 1.0, 0.3), lrc.Waypoint(7.0, 5.0, 1.2, 2.0)])
+    intr = lrc.Indoor8LineLidarIntrinsics(max_range=6.0, horizontal_res=1000)
+    tiny = lrc.TriangleMesh(np.array([[0, -5, -5], [0, 5, -5], [0, 0, 5.0], [9, -5, -5], [9, 5, -5], [9, 0, 5.0]]) + [4.0, 3, 1], [[0, 1, 2], [3, 4, 5]])
+    try:
+        for mesh in (c1["mesh"], tiny, lrc.TriangleMesh(tiny.vertices[:3], [[0, 1, 2]])):
+            ctx.set_option("variant", 5); ctx.set_option("block", 128)
+            ref = engine.simulate(poses, intr, mesh).numpy()
+            for var, blk, top in ((0, 128, 0), (1, 64, 0), (2, 32, 0), (3, 128, 0), (13, 128, 1), (13, 64, 4), (13, 128, 8)):
+                ctx.set_option("variant", var); ctx.set_option("block", blk)
+                if top:
+                    ctx.set_option("top_levels", top)
+                got = engine.simulate(poses, intr, mesh).numpy()
+                for k in ref:
+                    assert np.array_equal(got[k], ref[k]), (var, blk, top, k)
+    finally:
+        ctx.set_option("variant", 5); ctx.set_option("block", 128); ctx.set_option("top_levels", 6)
