@@ -28,6 +28,7 @@ struct lrc_ctx {
     float4* tris = nullptr;       // T x 3 float4 (48 B records, Morton order): (v0|orig id) (e1|0) (e2|0)
     uint32_t* labels = nullptr;   // T, original triangle order
     float4* top_table = nullptr;  // (2^LRC_TOP_LEVELS_MAX - 1) x 4 float4: copies of the top nodes in heap order
+    int64_t opt_stack_levels = 12;   // traversal-stack entries kept in shared memory by the VARIANT-bit-4 kernel
     int64_t opt_top_levels = 6;   // levels staged in shared memory by the VARIANT-bit-3 traversal kernel
     void* bvh_block = nullptr;    // one allocation [nodes | tris]: a single L2 access-policy window covers both
     size_t bvh_block_bytes = 0;

@@ -175,7 +175,8 @@ template <int MODE, bool COUNT, bool OUT_DENSE, int VARIANT>
 __global__ void __launch_bounds__(TRACE_THREADS, (VARIANT & 4) ? 16 : 1)   // VARIANT bit 2: cap registers at 32 for 64 warps per SM
 k_trace(RayGen g, FrameMath fm, const float4* __restrict__ nodes, const float4* __restrict__ tris, int64_t n, int has_tris,
         float4* __restrict__ hp, double* __restrict__ inc_out, unsigned* __restrict__ block_count, float* __restrict__ t_hit,
-        uint32_t* __restrict__ prim_id, unsigned long long* counters, const float4* __restrict__ top_table, int top_n)
+        uint32_t* __restrict__ prim_id, unsigned long long* counters, const float4* __restrict__ top_table, int top_n,
+        int stack_levels)
 {
     extern __shared__ float4 s_top[];
     if (VARIANT & 8) {      // stage the top of the tree (heap order, built by lrc_set_mesh) in shared memory
@@ -191,7 +192,7 @@ k_trace(RayGen g, FrameMath fm, const float4* __restrict__ nodes, const float4* 
         float t = LRC_INF;
         uint32_t id = LRC_MISS_ID;
         if (ray.keep && has_tris) {
-            trace_ray<VARIANT, COUNT>(nodes, tris, s_top, top_n, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, t, id, nn, nt);
+            trace_ray<VARIANT, COUNT>(nodes, tris, s_top, top_n, stack_levels, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, t, id, nn, nt);
             nr = 1;
             nh = id != LRC_MISS_ID;
         }
@@ -503,10 +504,11 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
     unsigned long long* counters = ctx->d_counters;
     const float4* top_table = ctx->top_table;
     const int top_n = (ctx->opt_variant & 8) ? (int)((1 << ctx->opt_top_levels) - 1) : 0;
-    cfg.dynamicSmemBytes = (size_t)top_n * 64;
+    const int stack_levels = (ctx->opt_variant & 16) ? (int)ctx->opt_stack_levels : 0;
+    cfg.dynamicSmemBytes = (ctx->opt_variant & 16) ? (size_t)stack_levels * LRC_SS_STRIDE * sizeof(int) : (size_t)top_n * 64;
     cudaError_t le = cudaSuccess;
 #define LRC_LAUNCH_TRACE(COUNT, VARIANT) \
-    le = cudaLaunchKernelEx(&cfg, k_trace<MODE, COUNT, DENSE, VARIANT>, g, fm, nodes, tris, n, has_tris, hp, inc, block_count, t_hit, prim, counters, top_table, top_n)
+    le = cudaLaunchKernelEx(&cfg, k_trace<MODE, COUNT, DENSE, VARIANT>, g, fm, nodes, tris, n, has_tris, hp, inc, block_count, t_hit, prim, counters, top_table, top_n, stack_levels)
     if (ctx->counting) {
         switch (ctx->opt_variant) {
             case 0: LRC_LAUNCH_TRACE(true, 0); break;
@@ -514,6 +516,7 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
             case 2: LRC_LAUNCH_TRACE(true, 2); break;
             case 5: LRC_LAUNCH_TRACE(true, 5); break;
             case 13: LRC_LAUNCH_TRACE(true, 13); break;
+            case 21: LRC_LAUNCH_TRACE(true, 21); break;
             default: LRC_LAUNCH_TRACE(true, 3); break;
         }
     } else {
@@ -523,6 +526,7 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
             case 2: LRC_LAUNCH_TRACE(false, 2); break;
             case 5: LRC_LAUNCH_TRACE(false, 5); break;
             case 13: LRC_LAUNCH_TRACE(false, 13); break;
+            case 21: LRC_LAUNCH_TRACE(false, 21); break;
             default: LRC_LAUNCH_TRACE(false, 3); break;
         }
     }
@@ -856,6 +860,11 @@ extern "C" int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value)
         return LRC_OK;
     }
     if (!strcmp(key, "l2_reset")) { LRC_CUDA(ctx, cudaSetDevice(ctx->device)); LRC_CUDA(ctx, cudaCtxResetPersistingL2Cache()); return LRC_OK; }
+    if (!strcmp(key, "stack_levels")) {
+        if (value < 1 || value > 48) return lrc_fail(ctx, LRC_ERR_INVALID, "stack_levels must be in [1, 48]");
+        ctx->opt_stack_levels = value;
+        return LRC_OK;
+    }
     if (!strcmp(key, "top_levels")) {
         if (value < 1 || value > LRC_TOP_LEVELS_MAX) return lrc_fail(ctx, LRC_ERR_INVALID, "top_levels must be in [1, 8]");
         ctx->opt_top_levels = value;
@@ -871,7 +880,7 @@ extern "C" int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value)
     }
     if (!strcmp(key, "kernel_timing")) { ctx->opt_kernel_timing = value != 0; ctx->kt_used = 0; return LRC_OK; }
     if (!strcmp(key, "variant")) {
-        if (value < 0 || (value > 3 && value != 5 && value != 13)) return lrc_fail(ctx, LRC_ERR_INVALID, "variant must be 0..3, 5 or 13");
+        if (value < 0 || (value > 3 && value != 5 && value != 13 && value != 21)) return lrc_fail(ctx, LRC_ERR_INVALID, "variant must be 0..3, 5, 13 or 21");
         ctx->opt_variant = value;
         return LRC_OK;
     }

@@ -112,15 +112,51 @@ __device__ __forceinline__ void leaf_test(const float4* __restrict__ tris, int l
     }
 }
 
+// Traversal stack.
+// StackLocal: per-thread array (local memory: lanes with different depths touch different 128 B lines).  An empty stack
+// pops the sentinel without touching memory.
+// StackShared (VARIANT bit 4): the first `levels` entries live in shared memory as [level][thread] -- one conflict-free
+// wavefront per access whatever the lanes' depths -- deeper entries spill to a local array.  Measured slower than the
+// local stack at every depth (profiles/r01c_smem_stack_sweep.jsonl); selectable, default off.
+#define LRC_SS_STRIDE 128      // threads per block of the traversal kernel (upper bound)
+// (The stack pointer is a separate scalar on purpose: as a member next to the dynamically indexed array it is demoted to
+// local memory with it -- measured +8 % kernel time.)
+struct StackLocal {
+    int a[LRC_STACK_DEPTH];
+    __device__ __forceinline__ void push(int& sp, int v) { a[sp++] = v; }
+    __device__ __forceinline__ int pop(int& sp) { return sp > 0 ? a[--sp] : LRC_SENTINEL; }
+};
+struct StackShared {
+    int a[LRC_STACK_DEPTH];
+    __device__ __forceinline__ void push(int& sp, int v, int* sm, int levels) { if (sp < levels) sm[sp * LRC_SS_STRIDE] = v; else a[sp - levels] = v; ++sp; }
+    __device__ __forceinline__ int pop(int& sp, int* sm, int levels)
+    {
+        if (sp == 0) return LRC_SENTINEL;
+        --sp;
+        return sp < levels ? sm[sp * LRC_SS_STRIDE] : a[sp - levels];
+    }
+};
+// uniform access for both policies: sm / levels are ignored by the local stack
+template <class STACK> struct StackOps;
+template <> struct StackOps<StackLocal> {
+    static __device__ __forceinline__ void push(StackLocal& st, int& sp, int v, int*, int) { st.push(sp, v); }
+    static __device__ __forceinline__ int pop(StackLocal& st, int& sp, int*, int) { return st.pop(sp); }
+};
+template <> struct StackOps<StackShared> {
+    static __device__ __forceinline__ void push(StackShared& st, int& sp, int v, int* sm, int levels) { st.push(sp, v, sm, levels); }
+    static __device__ __forceinline__ int pop(StackShared& st, int& sp, int* sm, int levels) { return st.pop(sp, sm, levels); }
+};
+
 // One step at an inner node: returns the next link (child to descend into, or a popped entry, or the sentinel).
 // Top of the tree staged in shared memory (VARIANT bit 3): `s_top` holds the first top_n node records in HEAP order
 // (entry h has its children at 2h+1 / 2h+2), copied there by every block; a link >= LRC_TOP_BASE addresses that table.
 // Records are unmodified copies, so a child link is redirected into the table on the fly when its heap slot exists.
 #define LRC_TOP_BASE 0x40000000   // node ids are < 2^30 (lrc_set_mesh)
 
-template <bool COUNT, bool WIDE, bool TOP>
+template <bool COUNT, bool WIDE, bool TOP, class STACK>
 __device__ __forceinline__ int inner_step(const float4* __restrict__ nodes, const float4* s_top, int top_n, int cur,
-                                          const RaySlab& s, float best_t, int* stack, int& sp, unsigned& n_nodes)
+                                          const RaySlab& s, float best_t, STACK& stack, int& sp, int* sm, int levels,
+                                          unsigned& n_nodes)
 {
     float4 n0, n1, n2;
     int l0, l1;
@@ -151,28 +187,28 @@ __device__ __forceinline__ int inner_step(const float4* __restrict__ nodes, cons
     const bool h1 = slab_ch(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, s, best_t, t1);
     if (h0 && h1) {
         const bool swp = t1 < t0;              // nearer child first, farther one on the stack
-        stack[sp++] = swp ? l0 : l1;
+        StackOps<STACK>::push(stack, sp, swp ? l0 : l1, sm, levels);
         return swp ? l1 : l0;
     }
     if (h0) return l0;
     if (h1) return l1;
-    return sp > 0 ? stack[--sp] : LRC_SENTINEL;
+    return StackOps<STACK>::pop(stack, sp, sm, levels);
 }
 
 // Stack-based closest-hit traversal.  VARIANT bit 0: 0 = one node (inner or leaf) per loop trip ("if-if"),
 // 1 = "while-while" -- run down inner nodes until a leaf (or the end) is reached, then test the leaf.
 // VARIANT bit 1: node records fetched with 256-bit loads.  VARIANT bit 2 (scan.cu): 32-register cap (64 warps per SM).
 // VARIANT bit 3: the first top_n nodes (heap order) are read from shared memory.
-template <int VARIANT, bool COUNT>
-__device__ __forceinline__ void trace_ray(const float4* __restrict__ nodes, const float4* __restrict__ tris,
-                                          const float4* s_top, int top_n, float ox,
-                                          float oy, float oz, float dx, float dy, float dz, float& best_t,
-                                          uint32_t& best_id, unsigned& n_nodes, unsigned& n_tris)
+// VARIANT bit 4: the first stack levels live in shared memory (StackShared).
+template <int VARIANT, bool COUNT, class STACK>
+__device__ __forceinline__ void trace_loop(const float4* __restrict__ nodes, const float4* __restrict__ tris,
+                                           const float4* s_top, int top_n, STACK& stack, int* sm, int levels, float ox,
+                                           float oy, float oz, float dx, float dy, float dz, float& best_t,
+                                           uint32_t& best_id, unsigned& n_nodes, unsigned& n_tris)
 {
     best_t = LRC_INF;
     best_id = LRC_MISS_ID;
     const RaySlab s = make_slab(ox, oy, oz, dx, dy, dz);
-    int stack[LRC_STACK_DEPTH];
     int sp = 0;
     constexpr bool WIDE = (VARIANT & 2) != 0;
     constexpr bool TOP = (VARIANT & 8) != 0;
@@ -180,21 +216,38 @@ __device__ __forceinline__ void trace_ray(const float4* __restrict__ nodes, cons
     if ((VARIANT & 1) == 0) {
         while (cur != LRC_SENTINEL) {
             if (cur >= 0) {
-                cur = inner_step<COUNT, WIDE, TOP>(nodes, s_top, top_n, cur, s, best_t, stack, sp, n_nodes);
+                cur = inner_step<COUNT, WIDE, TOP>(nodes, s_top, top_n, cur, s, best_t, stack, sp, sm, levels, n_nodes);
             } else {
                 if (COUNT) ++n_tris;
                 leaf_test(tris, cur, ox, oy, oz, dx, dy, dz, best_t, best_id);
-                cur = sp > 0 ? stack[--sp] : LRC_SENTINEL;
+                cur = StackOps<STACK>::pop(stack, sp, sm, levels);
             }
         }
     } else {
         while (cur != LRC_SENTINEL) {
-            while (cur >= 0) cur = inner_step<COUNT, WIDE, TOP>(nodes, s_top, top_n, cur, s, best_t, stack, sp, n_nodes);
+            while (cur >= 0) cur = inner_step<COUNT, WIDE, TOP>(nodes, s_top, top_n, cur, s, best_t, stack, sp, sm, levels, n_nodes);
             if (cur != LRC_SENTINEL) {
                 if (COUNT) ++n_tris;
                 leaf_test(tris, cur, ox, oy, oz, dx, dy, dz, best_t, best_id);
-                cur = sp > 0 ? stack[--sp] : LRC_SENTINEL;
+                cur = StackOps<STACK>::pop(stack, sp, sm, levels);
             }
         }
+    }
+}
+
+// `smem` = the block's dynamic shared memory: the heap-ordered top table (bit 3) or the shared stack levels (bit 4).
+template <int VARIANT, bool COUNT>
+__device__ __forceinline__ void trace_ray(const float4* __restrict__ nodes, const float4* __restrict__ tris,
+                                          const float4* smem, int top_n, int stack_levels, float ox,
+                                          float oy, float oz, float dx, float dy, float dz, float& best_t,
+                                          uint32_t& best_id, unsigned& n_nodes, unsigned& n_tris)
+{
+    if (VARIANT & 16) {
+        StackShared st;
+        int* sm = reinterpret_cast<int*>(const_cast<float4*>(smem)) + threadIdx.x;   // this thread's column of the shared table
+        trace_loop<VARIANT, COUNT>(nodes, tris, smem, top_n, st, sm, stack_levels, ox, oy, oz, dx, dy, dz, best_t, best_id, n_nodes, n_tris);
+    } else {
+        StackLocal st;
+        trace_loop<VARIANT, COUNT>(nodes, tris, smem, top_n, st, nullptr, 0, ox, oy, oz, dx, dy, dz, best_t, best_id, n_nodes, n_tris);
     }
 }

@@ -334,12 +334,15 @@ def test_all_traversal_variants_and_block_sizes_give_identical_bits(engine, lrc,
         for mesh in (c1["mesh"], tiny, lrc.TriangleMesh(tiny.vertices[:3], [[0, 1, 2]])):
             ctx.set_option("variant", 5); ctx.set_option("block", 128)
             ref = engine.simulate(poses, intr, mesh).numpy()
-            for var, blk, top in ((0, 128, 0), (1, 64, 0), (2, 32, 0), (3, 128, 0), (13, 128, 1), (13, 64, 4), (13, 128, 8)):
+            for var, blk, top in ((0, 128, 0), (1, 64, 0), (2, 32, 0), (3, 128, 0), (13, 128, 1), (13, 64, 4), (13, 128, 8),
+                                  (21, 128, -1), (21, 64, -3), (21, 128, -40)):
                 ctx.set_option("variant", var); ctx.set_option("block", blk)
-                if top:
+                if top > 0:
                     ctx.set_option("top_levels", top)
+                if top < 0:
+                    ctx.set_option("stack_levels", -top)
                 got = engine.simulate(poses, intr, mesh).numpy()
                 for k in ref:
                     assert np.array_equal(got[k], ref[k]), (var, blk, top, k)
     finally:
-        ctx.set_option("variant", 5); ctx.set_option("block", 128); ctx.set_option("top_levels", 6)
+        ctx.set_option("variant", 5); ctx.set_option("block", 128); ctx.set_option("top_levels", 6); ctx.set_option("stack_levels", 12)

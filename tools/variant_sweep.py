@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--variants", default="0,1,2,3")
     ap.add_argument("--blocks", default="32,64,128")
     ap.add_argument("--l2", default="0", help="comma list of l2_persist percentages")
+    ap.add_argument("--stack", default="12", help="comma list of stack_levels for the shared-memory-stack variants (bit 4)")
     ap.add_argument("--top", default="6", help="comma list of top_levels for the shared-memory variants (bit 3)")
     args = ap.parse_args()
     w, mesh, poses, intr = bench.make_workload(lrc, args.workload, 1)
@@ -45,10 +46,13 @@ def main():
     combos = []
     for var, l2 in itertools.product([int(x) for x in args.variants.split(",")], [int(x) for x in args.l2.split(",")]):
         for top in ([int(x) for x in args.top.split(",")] if var & 8 else [0]):
-            combos.append((var, l2, top))
-    for var, l2, top in combos:
+            for stk in ([int(x) for x in args.stack.split(",")] if var & 16 else [0]):
+                combos.append((var, l2, top, stk))
+    for var, l2, top, stk in combos:
         if top:
             ctx.set_option("top_levels", top)
+        if stk:
+            ctx.set_option("stack_levels", stk)
         for blk in [int(x) for x in args.blocks.split(",")]:
             ctx.set_option("variant", var)
             ctx.set_option("block", blk)
@@ -67,7 +71,7 @@ def main():
             sig = (m, int(bufs["prim"][:m].to(torch.int64).sum().item()), float(bufs["xyz"][:m].double().sum().item()))
             if ref is None:
                 ref = sig
-            print(json.dumps({"variant": var, "block": blk, "l2_persist": l2, "top_levels": top, "trace_ms": round(float(np.mean(tr)), 4),
+            print(json.dumps({"variant": var, "block": blk, "l2_persist": l2, "top_levels": top, "stack_levels": stk, "trace_ms": round(float(np.mean(tr)), 4),
                               "trace_ms_min": round(float(np.min(tr)), 4), "compact_ms": round(float(np.mean(cp)), 4),
                               "Mrays_s_trace": round(P * n_frame / np.mean(tr) / 1e3, 1), "same_output": sig == ref}), flush=True)
 
