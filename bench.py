@@ -266,6 +266,8 @@ def run_ours(args):
     ctx = engine.ctx
     if args.variant is not None:
         ctx.set_option("variant", args.variant)
+    if args.node_format is not None:
+        ctx.set_option("node_format", args.node_format)
     if args.l2_persist is not None:
         ctx.set_option("l2_persist", args.l2_persist)
     l2_pct = int(args.l2_persist) if args.l2_persist is not None else ctx.default_l2_persist()
@@ -503,6 +505,7 @@ def main():
     ap.add_argument("--gather-ramp", type=int, default=None, help="N>1: first chunk = regular chunk / ramp")
     ap.add_argument("--push-blocks", type=int, default=None, help="N>1: blocks per target of the exchange kernel")
     ap.add_argument("--e2e-chunk", type=int, default=None, help="poses per chunk of the pipelined e2e path")
+    ap.add_argument("--node-format", type=int, default=None, help="0 = 64 B float node records, 1 = 32 B 16-bit records")
     ap.add_argument("--l2-persist", type=int, default=None, help="percent of the max persisting-L2 set-aside reserved for the BVH window (0 = off)")
     ap.add_argument("--variant", type=int, default=None, help="traversal kernel variant (lrc_set_option)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")

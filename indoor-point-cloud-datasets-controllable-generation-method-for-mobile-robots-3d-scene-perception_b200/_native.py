@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "liblrc.so")
+# LRC_LIBRARY_PATH points at an alternative build of the same library (kernel experiments); there is still no fallback
+LIB_PATH = os.environ.get("LRC_LIBRARY_PATH") or os.path.join(_HERE, "csrc", "liblrc.so")
 
 MISS_ID = 0xFFFFFFFF
 

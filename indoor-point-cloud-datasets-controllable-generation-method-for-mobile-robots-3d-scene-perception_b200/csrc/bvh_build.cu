@@ -324,9 +324,29 @@ __device__ __forceinline__ void write_node(float4* __restrict__ rec, const float
     rec[3] = make_float4(__int_as_float(link0), __int_as_float(link1), 0.f, 0.f);
 }
 
+// 32-byte record: (x0 y0 z0 link0)(x1 y1 z1 link1), each axis word = qlo | qhi << 16 with x = o + q * s.
+// Conservative by construction: lo is rounded down and hi up to the cell grid and both are moved out by one more cell,
+// which covers the rounding of this division (< 0.01 cell) and of the traversal's decode (< 0.6 cell, traverse.cuh).
+__device__ __forceinline__ unsigned quant_axis(float lo, float hi, float o, float s)
+{
+    int a = (int)floorf((lo - o) / s) - 1, b = (int)ceilf((hi - o) / s) + 1;
+    a = min(max(a, 0), 65535);
+    b = min(max(b, 0), 65535);
+    return (unsigned)a | ((unsigned)b << 16);
+}
+
+__device__ __forceinline__ void write_node_q(float4* __restrict__ rec, const NodeQ& q, const float4 l0, const float4 h0,
+                                             const float4 l1, const float4 h1, int link0, int link1)
+{
+    rec[0] = make_float4(__uint_as_float(quant_axis(l0.x, h0.x, q.o[0], q.s[0])), __uint_as_float(quant_axis(l0.y, h0.y, q.o[1], q.s[1])),
+                         __uint_as_float(quant_axis(l0.z, h0.z, q.o[2], q.s[2])), __int_as_float(link0));
+    rec[1] = make_float4(__uint_as_float(quant_axis(l1.x, h1.x, q.o[0], q.s[0])), __uint_as_float(quant_axis(l1.y, h1.y, q.o[1], q.s[1])),
+                         __uint_as_float(quant_axis(l1.z, h1.z, q.o[2], q.s[2])), __int_as_float(link1));
+}
+
 __global__ void k_refit(int n, const int* __restrict__ parent_leaf, const int* __restrict__ parent_node,
                         const int2* __restrict__ children, const float4* leaf_lo, const float4* leaf_hi, float4* node_lo,
-                        float4* node_hi, int* flags, float4* __restrict__ nodes_out, BuildMeta* meta)
+                        float4* node_hi, int* flags, float4* __restrict__ nodes_out, BuildMeta* meta, int format, NodeQ nq)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -342,7 +362,8 @@ __global__ void k_refit(int n, const int* __restrict__ parent_leaf, const int* _
         float4 hi = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.f);
         node_lo[cur] = lo;
         node_hi[cur] = hi;
-        write_node(nodes_out + 4 * (int64_t)cur, l0, h0, l1, h1, ch.x, ch.y);
+        if (format == 0) write_node(nodes_out + 4 * (int64_t)cur, l0, h0, l1, h1, ch.x, ch.y);
+        else write_node_q(nodes_out + 2 * (int64_t)cur, nq, l0, h0, l1, h1, ch.x, ch.y);
         int up = parent_node[cur];
         if (up < 0) {
             meta->height = (int)height;
@@ -355,10 +376,12 @@ __global__ void k_refit(int n, const int* __restrict__ parent_leaf, const int* _
 }
 
 // T == 1: a root record whose two links both point at the only leaf (testing it twice is harmless)
-__global__ void k_single_leaf_root(const float4* leaf_lo, const float4* leaf_hi, float4* nodes_out, BuildMeta* meta)
+__global__ void k_single_leaf_root(const float4* leaf_lo, const float4* leaf_hi, float4* nodes_out, BuildMeta* meta, int format,
+                                   NodeQ nq)
 {
     float4 l = leaf_lo[0], h = leaf_hi[0];
-    write_node(nodes_out, l, h, l, h, ~0, ~0);
+    if (format == 0) write_node(nodes_out, l, h, l, h, ~0, ~0);
+    else write_node_q(nodes_out, nq, l, h, l, h, ~0, ~0);
     meta->height = 1;
     meta->root_lo[0] = l.x; meta->root_lo[1] = l.y; meta->root_lo[2] = l.z;
     meta->root_hi[0] = h.x; meta->root_hi[1] = h.y; meta->root_hi[2] = h.z;
@@ -388,10 +411,20 @@ __global__ void __launch_bounds__(256) k_top_table(const float4* __restrict__ no
 }
 
 // SAH diagnostic: sum of the surface areas of every child box stored in the node records
-__global__ void k_sah_sum(const float4* __restrict__ nodes, int64_t n_nodes, double* out)
+__global__ void k_sah_sum(const float4* __restrict__ nodes, int64_t n_nodes, double* out, int format, NodeQ nq)
 {
     double acc = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_nodes; i += (int64_t)gridDim.x * blockDim.x) {
+        if (format == 1) {
+            for (int c = 0; c < 2; ++c) {
+                const float4 r = nodes[2 * i + c];
+                const unsigned w[3] = {__float_as_uint(r.x), __float_as_uint(r.y), __float_as_uint(r.z)};
+                double e[3];
+                for (int k = 0; k < 3; ++k) e[k] = (double)((w[k] >> 16) - (w[k] & 0xffffu)) * nq.s[k];
+                acc += 2.0 * (e[0] * e[1] + e[1] * e[2] + e[2] * e[0]);
+            }
+            continue;
+        }
         const float4 n0 = nodes[4 * i], n1 = nodes[4 * i + 1], n2 = nodes[4 * i + 2];
         acc += 8.0 * ((double)n0.w * n1.x + (double)n1.x * n1.y + (double)n1.y * n0.w);   // child 0: h = (n0.w, n1.x, n1.y)
         acc += 8.0 * ((double)n2.y * n2.z + (double)n2.z * n2.w + (double)n2.w * n2.y);   // child 1: h = (n2.y, n2.z, n2.w)
@@ -422,8 +455,9 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
         return LRC_OK;
     }
     const int64_t n_nodes = T > 1 ? T - 1 : 1;
+    const int format = (int)ctx->opt_node_format;
     {
-        const size_t nodes_bytes = align_up(sizeof(float4) * 4 * (size_t)n_nodes, 256);
+        const size_t nodes_bytes = align_up(sizeof(float4) * (format == 0 ? 4 : 2) * (size_t)n_nodes, 256);
         const size_t tris_bytes = align_up(sizeof(float4) * 3 * (size_t)T, 256);
         int rcb = lrc_grow(ctx, &ctx->bvh_block, &ctx->bvh_block_bytes, nodes_bytes + tris_bytes);
         if (rcb) return rcb;
@@ -492,6 +526,16 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
     // Leaf boxes are padded by 2^-17 of the scene scale (0.19 mm for a 25 m room): float32 rounding of
     // the slab test (~1e-6 m) and of the Moller-Trumbore acceptance can then never cull a valid hit.
     const float pad = ldexpf(fmaxf(ext, amax), -17);
+    // cell grid of the 32-byte node format: 65533 cells span the scene plus a margin of two pads on either side, so
+    // every padded box quantises to [1, 65534] and the +-1 cell widening stays inside 16 bits
+    NodeQ nq;
+    for (int k = 0; k < 3; ++k) {
+        const float span = (shi[k] - slo[k]) + 8.f * pad;
+        nq.o[k] = slo[k] - 4.f * pad;
+        nq.s[k] = fmaxf(span, 1e-6f) / 65533.f;
+    }
+    ctx->nodeq = nq;
+    ctx->node_format = format;
 
     k_morton<<<gT, TB, 0, stream>>>(verts, tris, T, meta, k0, v0);
     LRC_CHECK_LAUNCH(ctx, "k_morton");
@@ -512,7 +556,7 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
     k_leaf_init<<<gT, TB, 0, stream>>>(verts, tris, T, vin, pad, ctx->tris, leaf_lo, leaf_hi);
     LRC_CHECK_LAUNCH(ctx, "k_leaf_init");
     if (T == 1) {
-        k_single_leaf_root<<<1, 1, 0, stream>>>(leaf_lo, leaf_hi, ctx->nodes, meta);
+        k_single_leaf_root<<<1, 1, 0, stream>>>(leaf_lo, leaf_hi, ctx->nodes, meta, format, nq);
         LRC_CHECK_LAUNCH(ctx, "k_single_leaf_root");
     } else {
         const unsigned gN = (unsigned)((T - 1 + TB - 1) / TB);
@@ -520,14 +564,16 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
         LRC_CHECK_LAUNCH(ctx, "k_hierarchy");
         LRC_CUDA(ctx, cudaMemsetAsync(flags, 0, sizeof(int) * n_nodes, stream));
         k_refit<<<gT, TB, 0, stream>>>((int)T, parent_leaf, parent_node, children, leaf_lo, leaf_hi, node_lo, node_hi, flags,
-                                       ctx->nodes, meta);
+                                       ctx->nodes, meta, format, nq);
         LRC_CHECK_LAUNCH(ctx, "k_refit");
     }
     {
         const int K = (1 << LRC_TOP_LEVELS_MAX) - 1;
         if (!ctx->top_table) LRC_CUDA(ctx, cudaMalloc((void**)&ctx->top_table, sizeof(float4) * 4 * K));
-        k_top_table<<<1, 256, 0, stream>>>(ctx->nodes, ctx->top_table, K);
-        LRC_CHECK_LAUNCH(ctx, "k_top_table");
+        if (format == 0) {      // the shared-memory top-of-tree variant exists for the float format only
+            k_top_table<<<1, 256, 0, stream>>>(ctx->nodes, ctx->top_table, K);
+            LRC_CHECK_LAUNCH(ctx, "k_top_table");
+        }
     }
     LRC_CUDA(ctx, cudaMemcpyAsync(&hm, meta, sizeof hm, cudaMemcpyDeviceToHost, stream));
     LRC_CUDA(ctx, cudaStreamSynchronize(stream));
@@ -543,7 +589,7 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
         ctx->root_area = 2.0 * ((double)ex * ey + (double)ey * ez + (double)ez * ex);
         inf.sah_cost = -1.f;   // computed on demand by lrc_bvh_get_info
     }
-    inf.bytes_nodes = (int64_t)sizeof(float4) * 4 * n_nodes;
+    inf.bytes_nodes = (int64_t)sizeof(float4) * (format == 0 ? 4 : 2) * n_nodes;
     inf.bytes_tris = (int64_t)sizeof(float4) * 3 * T;
     if (hm.height + 1 >= LRC_STACK_DEPTH) {
         char buf[32];
@@ -564,7 +610,7 @@ extern "C" int lrc_bvh_get_info(lrc_ctx* ctx, lrc_bvh_info* h_info)
         double* d_sum = nullptr;
         LRC_CUDA(ctx, cudaMalloc((void**)&d_sum, sizeof(double)));
         LRC_CUDA(ctx, cudaMemset(d_sum, 0, sizeof(double)));
-        k_sah_sum<<<296, 256>>>(ctx->nodes, ctx->info.num_nodes, d_sum);
+        k_sah_sum<<<296, 256>>>(ctx->nodes, ctx->info.num_nodes, d_sum, ctx->node_format, ctx->nodeq);
         LRC_CHECK_LAUNCH(ctx, "k_sah_sum");
         double h_sum = 0.0;
         LRC_CUDA(ctx, cudaMemcpy(&h_sum, d_sum, sizeof(double), cudaMemcpyDeviceToHost));

@@ -15,6 +15,10 @@
 #define LRC_MAX_GATHER 16         // == lrc_gather's array length
 #define LRC_TOP_LEVELS_MAX 8      // top-of-tree table: 2^8 - 1 = 255 node records in heap order (16 KB)
 
+// 32-byte node format (option "node_format" = 1): child boxes as 16-bit cell indices on a per-axis grid over the scene,
+// x = o + q * s.  See traverse.cuh (inner_step_q) and bvh_build.cu (write_node_q).
+struct NodeQ { float o[3]; float s[3]; };
+
 struct lrc_ctx {
     int device = 0;
     char err[512] = {0};
@@ -27,6 +31,9 @@ struct lrc_ctx {
     float4* nodes = nullptr;      // num_nodes x 4 float4 (64 B records)
     float4* tris = nullptr;       // T x 3 float4 (48 B records, Morton order): (v0|orig id) (e1|0) (e2|0)
     uint32_t* labels = nullptr;   // T, original triangle order
+    int64_t opt_node_format = 0;  // format the NEXT lrc_set_mesh builds: 0 = 64 B float boxes, 1 = 32 B 16-bit boxes
+    int node_format = 0;          // format of the tree that is resident now
+    NodeQ nodeq = {};
     float4* top_table = nullptr;  // (2^LRC_TOP_LEVELS_MAX - 1) x 4 float4: copies of the top nodes in heap order
     int64_t opt_stack_levels = 12;   // traversal-stack entries kept in shared memory by the VARIANT-bit-4 kernel
     int64_t opt_top_levels = 6;   // levels staged in shared memory by the VARIANT-bit-3 traversal kernel

@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, (VARIANT & 4) ? 16 : 1)   // VA
 k_trace(RayGen g, FrameMath fm, const float4* __restrict__ nodes, const float4* __restrict__ tris, int64_t n, int has_tris,
         float4* __restrict__ hp, double* __restrict__ inc_out, unsigned* __restrict__ block_count, float* __restrict__ t_hit,
         uint32_t* __restrict__ prim_id, unsigned long long* counters, const float4* __restrict__ top_table, int top_n,
-        int stack_levels)
+        int stack_levels, const __grid_constant__ NodeQ nq)
 {
     extern __shared__ float4 s_top[];
     if (VARIANT & 8) {      // stage the top of the tree (heap order, built by lrc_set_mesh) in shared memory
@@ -192,7 +192,7 @@ k_trace(RayGen g, FrameMath fm, const float4* __restrict__ nodes, const float4* 
         float t = LRC_INF;
         uint32_t id = LRC_MISS_ID;
         if (ray.keep && has_tris) {
-            trace_ray<VARIANT, COUNT>(nodes, tris, s_top, top_n, stack_levels, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, t, id, nn, nt);
+            trace_ray<VARIANT, COUNT>(nodes, tris, s_top, top_n, stack_levels, nq, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, t, id, nn, nt);
             nr = 1;
             nh = id != LRC_MISS_ID;
         }
@@ -503,30 +503,35 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
     const float4* tris = ctx->tris;
     unsigned long long* counters = ctx->d_counters;
     const float4* top_table = ctx->top_table;
-    const int top_n = (ctx->opt_variant & 8) ? (int)((1 << ctx->opt_top_levels) - 1) : 0;
-    const int stack_levels = (ctx->opt_variant & 16) ? (int)ctx->opt_stack_levels : 0;
-    cfg.dynamicSmemBytes = (ctx->opt_variant & 16) ? (size_t)stack_levels * LRC_SS_STRIDE * sizeof(int) : (size_t)top_n * 64;
+    const NodeQ nq = ctx->nodeq;
+    // the resident tree's record format selects the kernel family; the variant option tunes the float-format kernels
+    const int64_t variant = ctx->node_format == 1 ? 37 : ctx->opt_variant;
+    const int top_n = (variant & 8) ? (int)((1 << ctx->opt_top_levels) - 1) : 0;
+    const int stack_levels = (variant & 16) ? (int)ctx->opt_stack_levels : 0;
+    cfg.dynamicSmemBytes = (variant & 16) ? (size_t)stack_levels * LRC_SS_STRIDE * sizeof(int) : (size_t)top_n * 64;
     cudaError_t le = cudaSuccess;
 #define LRC_LAUNCH_TRACE(COUNT, VARIANT) \
-    le = cudaLaunchKernelEx(&cfg, k_trace<MODE, COUNT, DENSE, VARIANT>, g, fm, nodes, tris, n, has_tris, hp, inc, block_count, t_hit, prim, counters, top_table, top_n, stack_levels)
+    le = cudaLaunchKernelEx(&cfg, k_trace<MODE, COUNT, DENSE, VARIANT>, g, fm, nodes, tris, n, has_tris, hp, inc, block_count, t_hit, prim, counters, top_table, top_n, stack_levels, nq)
     if (ctx->counting) {
-        switch (ctx->opt_variant) {
+        switch (variant) {
             case 0: LRC_LAUNCH_TRACE(true, 0); break;
             case 1: LRC_LAUNCH_TRACE(true, 1); break;
             case 2: LRC_LAUNCH_TRACE(true, 2); break;
             case 5: LRC_LAUNCH_TRACE(true, 5); break;
             case 13: LRC_LAUNCH_TRACE(true, 13); break;
             case 21: LRC_LAUNCH_TRACE(true, 21); break;
+            case 37: LRC_LAUNCH_TRACE(true, 37); break;
             default: LRC_LAUNCH_TRACE(true, 3); break;
         }
     } else {
-        switch (ctx->opt_variant) {
+        switch (variant) {
             case 0: LRC_LAUNCH_TRACE(false, 0); break;
             case 1: LRC_LAUNCH_TRACE(false, 1); break;
             case 2: LRC_LAUNCH_TRACE(false, 2); break;
             case 5: LRC_LAUNCH_TRACE(false, 5); break;
             case 13: LRC_LAUNCH_TRACE(false, 13); break;
             case 21: LRC_LAUNCH_TRACE(false, 21); break;
+            case 37: LRC_LAUNCH_TRACE(false, 37); break;
             default: LRC_LAUNCH_TRACE(false, 3); break;
         }
     }
@@ -860,6 +865,11 @@ extern "C" int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value)
         return LRC_OK;
     }
     if (!strcmp(key, "l2_reset")) { LRC_CUDA(ctx, cudaSetDevice(ctx->device)); LRC_CUDA(ctx, cudaCtxResetPersistingL2Cache()); return LRC_OK; }
+    if (!strcmp(key, "node_format")) {
+        if (value != 0 && value != 1) return lrc_fail(ctx, LRC_ERR_INVALID, "node_format must be 0 (64 B float boxes) or 1 (32 B 16-bit boxes)");
+        ctx->opt_node_format = value;      // takes effect at the next lrc_set_mesh
+        return LRC_OK;
+    }
     if (!strcmp(key, "stack_levels")) {
         if (value < 1 || value > 48) return lrc_fail(ctx, LRC_ERR_INVALID, "stack_levels must be in [1, 48]");
         ctx->opt_stack_levels = value;

@@ -112,6 +112,50 @@ __device__ __forceinline__ void leaf_test(const float4* __restrict__ tris, int l
     }
 }
 
+// ---- 32-byte nodes: 16-bit boxes on the scene's cell grid (VARIANT bit 5) ----------------------------------------------
+// k_trace's ceiling is the L1 -> register return path: a 64 B float record is 56 B x 32 lanes = 14 cycles of data per
+// node and warp.  The quantised record halves that.  Plane coordinate x = o + q * s, so along one axis
+//     t(q) = (o + q*s - org) * inv = q * A + B          A = s * inv,  B = (o - org) * inv
+// A 16-bit q becomes a float without a conversion instruction: PRMT splices it into the mantissa of 2^23
+// (bits 0x4B000000 | q  ==  8388608 + q exactly), and the bias is folded into the constant:
+//     t(q) = fma(8388608 + q, A, B - 8388608 * A)
+// One PRMT + one FFMA per plane; which half-word is the near plane depends only on the ray's direction sign, so the PRMT
+// selectors are per-ray constants.  Error budget: the folded constant is rounded once at magnitude 2^23 * |A|, i.e. by at
+// most |A| / 2 = half a cell in t; everything else is ~1e-7 relative.  The builder widens every box by a full cell per
+// side (bvh_build.cu quant_axis), so culling stays conservative and results stay bit-identical to the float format.
+struct RaySlabQ {
+    float ax, ay, az;          // A
+    float bx, by, bz;          // B - 2^23 * A
+    unsigned sx, sy, sz;       // PRMT selector of the NEAR plane's half-word (0x7610 = low, 0x7632 = high)
+};
+
+__device__ __forceinline__ RaySlabQ make_slab_q(float ox, float oy, float oz, float dx, float dy, float dz, const NodeQ& q)
+{
+    RaySlabQ s;
+    const float ix = safe_inv(dx), iy = safe_inv(dy), iz = safe_inv(dz);
+    s.ax = __fmul_rn(q.s[0], ix); s.ay = __fmul_rn(q.s[1], iy); s.az = __fmul_rn(q.s[2], iz);
+    s.bx = __fmaf_rn(-8388608.f, s.ax, __fmul_rn(__fsub_rn(q.o[0], ox), ix));
+    s.by = __fmaf_rn(-8388608.f, s.ay, __fmul_rn(__fsub_rn(q.o[1], oy), iy));
+    s.bz = __fmaf_rn(-8388608.f, s.az, __fmul_rn(__fsub_rn(q.o[2], oz), iz));
+    s.sx = ix >= 0.f ? 0x7610u : 0x7632u;
+    s.sy = iy >= 0.f ? 0x7610u : 0x7632u;
+    s.sz = iz >= 0.f ? 0x7610u : 0x7632u;
+    return s;
+}
+
+__device__ __forceinline__ float q2f(unsigned w, unsigned sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)); }
+
+__device__ __forceinline__ bool slab_q(unsigned wx, unsigned wy, unsigned wz, const RaySlabQ& s, float tmax, float& tnear)
+{
+    const float n0 = fmaf(q2f(wx, s.sx), s.ax, s.bx), f0 = fmaf(q2f(wx, s.sx ^ 0x22u), s.ax, s.bx);
+    const float n1 = fmaf(q2f(wy, s.sy), s.ay, s.by), f1 = fmaf(q2f(wy, s.sy ^ 0x22u), s.ay, s.by);
+    const float n2 = fmaf(q2f(wz, s.sz), s.az, s.bz), f2 = fmaf(q2f(wz, s.sz ^ 0x22u), s.az, s.bz);
+    const float t0 = fmaxf(fmaxf(n0, n1), fmaxf(n2, 0.f));
+    const float t1 = fminf(fminf(f0, f1), fminf(f2, tmax));
+    tnear = t0;
+    return t0 <= t1;
+}
+
 // Traversal stack.
 // StackLocal: per-thread array (local memory: lanes with different depths touch different 128 B lines).  An empty stack
 // pops the sentinel without touching memory.
@@ -195,11 +239,33 @@ __device__ __forceinline__ int inner_step(const float4* __restrict__ nodes, cons
     return StackOps<STACK>::pop(stack, sp, sm, levels);
 }
 
+template <bool COUNT, class STACK>
+__device__ __forceinline__ int inner_step_q(const float4* __restrict__ nodes, int cur, const RaySlabQ& s, float best_t,
+                                            STACK& stack, int& sp, int* sm, int levels, unsigned& n_nodes)
+{
+    const uint4* np = reinterpret_cast<const uint4*>(nodes) + 2 * (int64_t)cur;
+    const uint4 a = __ldg(np), b = __ldg(np + 1);
+    if (COUNT) ++n_nodes;
+    float t0, t1;
+    const bool h0 = slab_q(a.x, a.y, a.z, s, best_t, t0);
+    const bool h1 = slab_q(b.x, b.y, b.z, s, best_t, t1);
+    const int l0 = (int)a.w, l1 = (int)b.w;
+    if (h0 && h1) {
+        const bool swp = t1 < t0;
+        StackOps<STACK>::push(stack, sp, swp ? l0 : l1, sm, levels);
+        return swp ? l1 : l0;
+    }
+    if (h0) return l0;
+    if (h1) return l1;
+    return StackOps<STACK>::pop(stack, sp, sm, levels);
+}
+
 // Stack-based closest-hit traversal.  VARIANT bit 0: 0 = one node (inner or leaf) per loop trip ("if-if"),
 // 1 = "while-while" -- run down inner nodes until a leaf (or the end) is reached, then test the leaf.
 // VARIANT bit 1: node records fetched with 256-bit loads.  VARIANT bit 2 (scan.cu): 32-register cap (64 warps per SM).
 // VARIANT bit 3: the first top_n nodes (heap order) are read from shared memory.
 // VARIANT bit 4: the first stack levels live in shared memory (StackShared).
+// VARIANT bit 5: 32-byte quantised node records (trace_loop_q; while-while only).
 template <int VARIANT, bool COUNT, class STACK>
 __device__ __forceinline__ void trace_loop(const float4* __restrict__ nodes, const float4* __restrict__ tris,
                                            const float4* s_top, int top_n, STACK& stack, int* sm, int levels, float ox,
@@ -235,14 +301,37 @@ __device__ __forceinline__ void trace_loop(const float4* __restrict__ nodes, con
     }
 }
 
+template <bool COUNT>
+__device__ __forceinline__ void trace_loop_q(const float4* __restrict__ nodes, const float4* __restrict__ tris, const NodeQ& nq,
+                                             float ox, float oy, float oz, float dx, float dy, float dz, float& best_t,
+                                             uint32_t& best_id, unsigned& n_nodes, unsigned& n_tris)
+{
+    best_t = LRC_INF;
+    best_id = LRC_MISS_ID;
+    const RaySlabQ s = make_slab_q(ox, oy, oz, dx, dy, dz, nq);
+    StackLocal stack;
+    int sp = 0;
+    int cur = 0;
+    while (cur != LRC_SENTINEL) {
+        while (cur >= 0) cur = inner_step_q<COUNT>(nodes, cur, s, best_t, stack, sp, nullptr, 0, n_nodes);
+        if (cur != LRC_SENTINEL) {
+            if (COUNT) ++n_tris;
+            leaf_test(tris, cur, ox, oy, oz, dx, dy, dz, best_t, best_id);
+            cur = StackOps<StackLocal>::pop(stack, sp, nullptr, 0);
+        }
+    }
+}
+
 // `smem` = the block's dynamic shared memory: the heap-ordered top table (bit 3) or the shared stack levels (bit 4).
 template <int VARIANT, bool COUNT>
 __device__ __forceinline__ void trace_ray(const float4* __restrict__ nodes, const float4* __restrict__ tris,
-                                          const float4* smem, int top_n, int stack_levels, float ox,
+                                          const float4* smem, int top_n, int stack_levels, const NodeQ& nq, float ox,
                                           float oy, float oz, float dx, float dy, float dz, float& best_t,
                                           uint32_t& best_id, unsigned& n_nodes, unsigned& n_tris)
 {
-    if (VARIANT & 16) {
+    if (VARIANT & 32) {
+        trace_loop_q<COUNT>(nodes, tris, nq, ox, oy, oz, dx, dy, dz, best_t, best_id, n_nodes, n_tris);
+    } else if (VARIANT & 16) {
         StackShared st;
         int* sm = reinterpret_cast<int*>(const_cast<float4*>(smem)) + threadIdx.x;   // this thread's column of the shared table
         trace_loop<VARIANT, COUNT>(nodes, tris, smem, top_n, st, sm, stack_levels, ox, oy, oz, dx, dy, dz, best_t, best_id, n_nodes, n_tris);

@@ -344,5 +344,14 @@ def test_all_traversal_variants_and_block_sizes_give_identical_bits(engine, lrc,
                 got = engine.simulate(poses, intr, mesh).numpy()
                 for k in ref:
                     assert np.array_equal(got[k], ref[k]), (var, blk, top, k)
+            # 32-byte quantised node records: a different tree encoding, the same bits out
+            ctx.set_option("node_format", 1); ctx._mesh_key = None
+            try:
+                got = engine.simulate(poses, intr, mesh).numpy()
+                assert engine.ctx.bvh_info()["bytes_nodes"] == 32 * engine.ctx.bvh_info()["num_nodes"]
+            finally:
+                ctx.set_option("node_format", 0); ctx._mesh_key = None
+            for k in ref:
+                assert np.array_equal(got[k], ref[k]), ("node_format 1", k)
     finally:
         ctx.set_option("variant", 5); ctx.set_option("block", 128); ctx.set_option("top_levels", 6); ctx.set_option("stack_levels", 12)

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--variants", default="0,1,2,3")
     ap.add_argument("--blocks", default="32,64,128")
+    ap.add_argument("--formats", default="0", help="comma list of node formats (0 = 64 B float, 1 = 32 B 16-bit); format 1 ignores --variants")
     ap.add_argument("--l2", default="0", help="comma list of l2_persist percentages")
     ap.add_argument("--stack", default="12", help="comma list of stack_levels for the shared-memory-stack variants (bit 4)")
     ap.add_argument("--top", default="6", help="comma list of top_levels for the shared-memory variants (bit 3)")
@@ -44,17 +45,30 @@ def main():
     ctx.set_option("kernel_timing", 1)
     import itertools
     combos = []
-    for var, l2 in itertools.product([int(x) for x in args.variants.split(",")], [int(x) for x in args.l2.split(",")]):
+    for fmt in [int(x) for x in args.formats.split(",")]:
+        if fmt == 1:
+            combos.append((37, 0, 0, 0))
+    for var, l2 in itertools.product([] if args.formats == "1" else [int(x) for x in args.variants.split(",")], [int(x) for x in args.l2.split(",")]):
         for top in ([int(x) for x in args.top.split(",")] if var & 8 else [0]):
             for stk in ([int(x) for x in args.stack.split(",")] if var & 16 else [0]):
                 combos.append((var, l2, top, stk))
+    cur_fmt = 0
     for var, l2, top, stk in combos:
+        fmt = 1 if var == 37 else 0
+        if fmt != cur_fmt:
+            ctx.set_option("node_format", fmt)
+            ctx.set_mesh_arrays(v, f, lab)
+            cur_fmt = fmt
+        if var == 37:
+            var_opt = 5
+        else:
+            var_opt = var
         if top:
             ctx.set_option("top_levels", top)
         if stk:
             ctx.set_option("stack_levels", stk)
         for blk in [int(x) for x in args.blocks.split(",")]:
-            ctx.set_option("variant", var)
+            ctx.set_option("variant", var_opt)
             ctx.set_option("block", blk)
             ctx.set_option("l2_persist", l2)
             tr, cp = [], []
