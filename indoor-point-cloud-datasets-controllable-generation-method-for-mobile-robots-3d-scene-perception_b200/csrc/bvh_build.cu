@@ -3,8 +3,8 @@
 //
 // Pipeline (all on the caller's stream, one synchronisation at the end to read back tree depth):
 //   k_vertex_bounds, k_check_indices   scene AABB (warp shuffles + ordered-int atomics), index validation
-//   k_morton         63-bit Morton code of each triangle's box centre (cubic cells, 21 bits/axis)
-//   radix sort       hand-written LSD sort of (u64 key, u32 triangle id), 8 bits x 8 passes:
+//   k_morton         Morton code of each triangle's box centre (cubic cells, 16 bits/axis kept of 21)
+//   radix sort       hand-written LSD sort of (u64 key, u32 triangle id), 8 bits x 6 passes (48 key bits):
 //                    k_rs_hist -> k_rs_scan -> k_rs_scatter (stable multi-split by warp match)
 //   k_leaf_init      48 B triangle records (v0|id, e1, e2) in Morton order + padded leaf boxes
 //   k_hierarchy      Karras 2012 binary radix tree over the sorted keys (ties broken by position)
@@ -112,7 +112,9 @@ __global__ void k_morton(const float* __restrict__ verts, const int32_t* __restr
         f = fminf(fmaxf(f, 0.f), 2097151.0f);
         q[k] = (uint32_t)f;
     }
-    keys[i] = (expand21(q[0]) << 2) | (expand21(q[1]) << 1) | expand21(q[2]);
+    // 16 bits per axis are kept (cells of 2^-16 of the scene, 0.3 mm for a 20 m room): the low 15 bits of the 63-bit code
+    // are dropped so that the sort needs 6 instead of 8 byte passes; equal keys are ordered by position (k_hierarchy)
+    keys[i] = ((expand21(q[0]) << 2) | (expand21(q[1]) << 1) | expand21(q[2])) & ~0x7fffull;
     vals[i] = (uint32_t)i;
 }
 
@@ -150,18 +152,31 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t* __restri
 
 __global__ void __launch_bounds__(1024) k_rs_scan(unsigned* __restrict__ a, int64_t M)
 {
-    // exclusive scan of M counters by one block, 4 per thread per trip (M = 256 * number of sort tiles)
+    // exclusive scan of M counters by one block, 16 per thread per trip as 4 x uint4 (M = 256 * number of sort tiles,
+    // the array is 256 B aligned)
+    constexpr int ITEMS = 16;
     __shared__ unsigned warp_sums[32];
     __shared__ unsigned carry;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry = 0u;
     __syncthreads();
-    for (int64_t base = 0; base < M; base += 4096) {
-        const int64_t idx = base + 4 * (int64_t)threadIdx.x;
-        unsigned v[4];
+    for (int64_t base = 0; base < M; base += 1024 * ITEMS) {
+        const int64_t idx = base + (int64_t)ITEMS * threadIdx.x;
+        unsigned v[ITEMS];
+        const bool full = idx + ITEMS <= M;
+        if (full) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = idx + k < M ? a[idx + k] : 0u;
-        const unsigned mine = v[0] + v[1] + v[2] + v[3];
+            for (int k = 0; k < ITEMS / 4; ++k) {
+                const uint4 q = reinterpret_cast<const uint4*>(a + idx)[k];
+                v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) v[k] = idx + k < M ? a[idx + k] : 0u;
+        }
+        unsigned mine = 0u;
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) mine += v[k];
         unsigned incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -181,10 +196,22 @@ __global__ void __launch_bounds__(1024) k_rs_scan(unsigned* __restrict__ a, int6
         }
         __syncthreads();
         unsigned run = incl - mine + warp_sums[w] + carry;
+        if (full) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (idx + k < M) a[idx + k] = run;
-            run += v[k];
+            for (int k = 0; k < ITEMS / 4; ++k) {
+                uint4 q;
+                q.x = run; run += v[4 * k];
+                q.y = run; run += v[4 * k + 1];
+                q.z = run; run += v[4 * k + 2];
+                q.w = run; run += v[4 * k + 3];
+                reinterpret_cast<uint4*>(a + idx)[k] = q;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) {
+                if (idx + k < M) a[idx + k] = run;
+                run += v[k];
+            }
         }
         __syncthreads();
         if (threadIdx.x == 1023) carry = run;
@@ -541,8 +568,8 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
     LRC_CHECK_LAUNCH(ctx, "k_morton");
     uint64_t *kin = k0, *kout = k1;
     uint32_t *vin = v0, *vout = v1;
-    for (int pass = 0; pass < 8; ++pass) {
-        const int shift = 8 * pass;
+    for (int pass = 0; pass < 6; ++pass) {       // key bits 15..62 (k_morton clears the low 15)
+        const int shift = 15 + 8 * pass;
         k_rs_hist<<<nb, RS_THREADS, 0, stream>>>(kin, T, shift, hist, nb);
         LRC_CHECK_LAUNCH(ctx, "k_rs_hist");
         k_rs_scan<<<1, 1024, 0, stream>>>(hist, (int64_t)256 * nb);
