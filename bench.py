@@ -252,6 +252,10 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
+    if world > 1 and not args.no_numa_bind:
+        from lrc_b200.distributed import bind_to_gpu_numa_node
+        numa = bind_to_gpu_numa_node(local)      # before any pinned allocation: staging buffers on the GPU's own socket
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -467,7 +471,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['desc']}", "tris": int(len(tris)), "rays_per_frame": n_frame,
-                       "poses_per_gpu": P, "poses_total": int(len(poses_all)), "parallelism": f"pose-sharded x{world}, replicated BVH",
+                       "poses_per_gpu": P, "poses_total": int(len(poses_all)), "parallelism": f"pose-sharded x{world}, replicated BVH", "numa_node_rank0": numa,
                        "l2": "flushed between timed iterations (256 MiB fill" + (", persisting lines reset first)" if l2_pct else ")"),
                        "l2_persist_pct": l2_pct, "noise": bool(w["noise"]),
                        "collective": ("none" if world == 1 else
@@ -505,6 +509,7 @@ def main():
     ap.add_argument("--gather-ramp", type=int, default=None, help="N>1: first chunk = regular chunk / ramp")
     ap.add_argument("--push-blocks", type=int, default=None, help="N>1: blocks per target of the exchange kernel")
     ap.add_argument("--e2e-chunk", type=int, default=None, help="poses per chunk of the pipelined e2e path")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N>1: do not pin each rank to its GPU's NUMA node")
     ap.add_argument("--node-format", type=int, default=None, help="0 = 64 B float node records, 1 = 32 B 16-bit records")
     ap.add_argument("--l2-persist", type=int, default=None, help="percent of the max persisting-L2 set-aside reserved for the BVH window (0 = off)")
     ap.add_argument("--variant", type=int, default=None, help="traversal kernel variant (lrc_set_option)")
