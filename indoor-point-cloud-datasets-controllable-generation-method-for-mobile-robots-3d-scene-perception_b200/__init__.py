@@ -11,12 +11,13 @@ The directory name contains hyphens, so import it through the alias package::
 Sub-packages keep the reference's module names: ``lidar`` (sensor model) and ``raycast_engine`` (engine).
 Importing the package needs neither a GPU nor the built library; creating an engine needs both.
 """
-from . import lidar, post, raycast_engine, synthetic, trajectory
+from . import lidar, post, raycast_engine, simulator, synthetic, trajectory
 from .core import (Context, NoiseConfig, ScanResult, TriangleMesh, get_context, mesh_arrays, pack_labels,
                    rays_per_frame, unpack_labels)
 from .lidar import (DualAxisLidar, DualAxisLidarIntrinsics, Indoor8LineLidarIntrinsics, IndoorLidar, LidarIntrinsics,
                     create_lidar, get_lidar_type)
 from .raycast_engine import RaycastEngineBase, RaycastEngineGPU
+from .simulator import SimFrame, SimRun, room_bounds_of, room_volume, run_simulation
 from .post import (LabelTransfer, ScanQuality, SimulationStats, frame_statistics, read_labeled_ply, scan_quality, simulation_stats,
                    write_labeled_ply)
 from .trajectory import AutoTrajectoryGenerator, TrajectoryQuality, Waypoint, poses_from_waypoints, shard_range
@@ -31,6 +32,6 @@ __all__ = [
     "unpack_labels", "rays_per_frame",
     "LidarIntrinsics", "Indoor8LineLidarIntrinsics", "DualAxisLidarIntrinsics", "IndoorLidar", "DualAxisLidar",
     "create_lidar", "get_lidar_type",
-    "RaycastEngineBase", "RaycastEngineGPU",
+    "RaycastEngineBase", "RaycastEngineGPU", "run_simulation", "SimRun", "SimFrame", "room_bounds_of", "room_volume",
     "Waypoint", "poses_from_waypoints", "shard_range", "AutoTrajectoryGenerator", "TrajectoryQuality",
 ]
