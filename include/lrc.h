@@ -155,9 +155,10 @@ int lrc_scan_dual_axis(lrc_ctx* ctx, const double* poses, int64_t P, const lrc_d
 /* ---- the same, with HOST buffers (the reference-facing call: numpy in, numpy out) -------------- */
 /* h_poses: P x 16 float64 on the host.  h_out: an lrc_out whose pointers are HOST memory (page-locked memory makes
  * the copies asynchronous; pageable memory works, slower).  The trajectory is cut into chunks of `chunk_poses` poses
- * (0 = automatic); every chunk's kernels are enqueued at once on an internal stream and each chunk's compacted
- * records are copied back on a second stream as soon as that chunk is finished, so the PCIe transfer overlaps the
- * traversal of later chunks.  Synchronous: on return every output is on the host and *h_num_points is set.
+ * (0 = automatic: a first chunk of ~0.5M rays, each following chunk twice as long, so that the PCIe copy -- the long
+ * pole -- starts early and then moves few, large pieces); every chunk's kernels are enqueued at once on an internal
+ * stream and each chunk's compacted records are copied back on a second stream as soon as that chunk is finished, so
+ * the PCIe transfer overlaps the traversal of later chunks.  Synchronous: on return every output is on the host and *h_num_points is set.
  * These two calls do NOT use the caller's stream. */
 int lrc_scan_single_axis_host(lrc_ctx* ctx, const double* h_poses, int64_t P, const lrc_single_axis* h_sensor,
                               const lrc_noise* h_noise, lrc_out* h_out, int64_t chunk_poses, int64_t* h_num_points);
@@ -280,9 +281,17 @@ int64_t lrc_launch_count(const lrc_ctx* ctx);
  * chunks (*h_launches = number of chunks = k_trace launches).  Requires lrc_set_option(ctx, "kernel_timing", 1)
  * before the scan; synchronises on the recorded events.  This is what bench.py's roofline divides by. */
 int lrc_kernel_times(lrc_ctx* ctx, double* h_trace_ms, double* h_compact_ms, int32_t* h_launches);
-/* Tuning knobs: "variant" (traversal loop shape), "block", "chunk_rays", "gather_chunks", "push_blocks",
- * "kernel_timing", "l2_persist" (percent of the device's maximum persisting-L2 set-aside reserved for an access-policy
- * window over the BVH records on every k_trace launch; 0 = off), "l2_reset" (demote all persisting lines now).
+/* Tuning knobs (defaults are the measured best; none of them changes a result bit):
+ *   "variant"       traversal kernel: bit 0 while-while loop, bit 1 256-bit node loads, bit 2 32-register build,
+ *                   bit 3 top of the tree in shared memory ("top_levels" 1..8), bit 4 stack in shared memory
+ *                   ("stack_levels" 1..48); accepted values 0..3, 5 (default), 13, 21
+ *   "node_format"   record format built by the NEXT lrc_set_mesh: 0 = 64 B float boxes (default), 1 = 32 B 16-bit boxes
+ *   "block"         threads per traversal block (32 / 64 / 128)
+ *   "chunk_rays"    rays per traversal chunk (bounds the 24 B/ray scratch)
+ *   "gather_chunks", "gather_ramp", "push_blocks"   pose chunks / short first chunk / exchange blocks of the all-gather
+ *   "kernel_timing" record CUDA events around k_trace and the compaction (lrc_kernel_times)
+ *   "l2_persist"    percent of the device's maximum persisting-L2 set-aside reserved for an access-policy window over
+ *                   the BVH records on every k_trace launch (0 = off, default); "l2_reset" demotes persisting lines now
  * Unknown keys -> LRC_ERR_INVALID. */
 int lrc_default_l2_persist(void);
 int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value);
