@@ -441,10 +441,15 @@ __device__ __forceinline__ void push_words(const uint32_t* __restrict__ src, uin
     if (tid < n - tail0) dst[tail0 + tid] = __ldcg(src + tail0 + tid);
     const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
     uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+    // the exchange is bound by bytes in flight towards each target (NVLink round trip ~ microseconds), not by SM count:
+    // eight 16-byte vectors per thread are loaded before the first store is issued
     int64_t i = tid;
-    for (; i + 3 * nthreads < nvec; i += 4 * nthreads) {            // four vectors in flight per thread
-        const uint4 a = __ldcg(s4 + i), b = __ldcg(s4 + i + nthreads), c = __ldcg(s4 + i + 2 * nthreads), d = __ldcg(s4 + i + 3 * nthreads);
-        __stcs(d4 + i, a); __stcs(d4 + i + nthreads, b); __stcs(d4 + i + 2 * nthreads, c); __stcs(d4 + i + 3 * nthreads, d);
+    for (; i + 7 * nthreads < nvec; i += 8 * nthreads) {
+        uint4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = __ldcg(s4 + i + k * nthreads);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) __stcs(d4 + i + k * nthreads, v[k]);
     }
     for (; i < nvec; i += nthreads) __stcs(d4 + i, __ldcg(s4 + i));
 }
