@@ -12,12 +12,15 @@ ray generation -> LBVH traversal -> fused epilogue (labels, range filter, incide
   e2e     same metric through the reference-facing API with HOST buffers: per step the mesh is uploaded and its
           LBVH rebuilt (the reference rebuilds its scene for every frame, raycast_engine_cpu.py:46-47; we do it once
           per trajectory), poses go H2D from pinned memory, points + incident angles + labels come back D2H
-  roofline  algorithmic bytes per ray (counted node / triangle records x 64 / 48 B + label + output) x rays/s
-            against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  roofline  the dominant kernel (k_trace) alone: algorithmic bytes of one launch (counted node / triangle records x
+            64 / 48 B + 24 B scratch per ray) / its device time from CUDA events recorded inside the library on the launching
+            stream, against the measured HBM copy bandwidth (MEASURED_PEAKS.json); traffic = DRAM bytes of one launch from
+            the committed ncu capture (profiles/traffic.json)
   cpu_baseline  the CPU oracle (a port: Open3D/Embree is absent) on this box's cores, bounded sample
 
 N > 1 (torchrun): poses are sharded contiguously across ranks with a replicated mesh/BVH (weak scaling: 100
-poses per GPU) and the compacted clouds are all-gathered over NCCL inside the timed region.
+poses per GPU); every rank's compacted cloud is all-gathered inside the timed region -- by default by the library's
+exchange kernel over NVLink peer memory (CUDA IPC), overlapped with traversal; --gather nccl uses NCCL instead.
 """
 from __future__ import annotations
 
@@ -338,14 +341,9 @@ def run_ours(args):
         else:
             ctx.scan_enqueue(poses_d, intr, noise, bufs)
 
-    def gather_step():
-        pass
-
     for _ in range(max(args.warmup, 3)):
         cold_l2(1)
         one_step()
-        if world > 1:
-            gather_step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -359,8 +357,6 @@ def run_ours(args):
         cold_l2(s)                                         # evict the BVH from L2 between timed iterations
         starts[s].record()
         one_step()
-        if world > 1:
-            gather_step()
         ends[s].record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
