@@ -88,6 +88,7 @@ struct lrc_ctx {
     void* ci_meta = nullptr; size_t ci_meta_bytes = 0;
     void* ci_start = nullptr; size_t ci_start_bytes = 0;
     void* ci_sorted = nullptr; size_t ci_sorted_bytes = 0;
+    void* cg_scratch = nullptr; size_t cg_scratch_bytes = 0;     // lrc_grid_connectivity's own scratch
     double ci_ox = 0, ci_oy = 0, ci_cell = 0;
     int ci_nbx = 0, ci_nby = 0;
 

@@ -276,9 +276,9 @@ extern "C" int lrc_grid_connectivity(lrc_ctx* ctx, const double* xs, int32_t nx,
     if (n >= (int64_t)1 << 30) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_grid_connectivity: grid too large");
     LRC_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t stream = (cudaStream_t)stream_;
-    int rc = lrc_grow(ctx, &ctx->post_scratch, &ctx->post_scratch_bytes, sizeof(int) * (size_t)(3 * n + 4));
+    int rc = lrc_grow(ctx, &ctx->cg_scratch, &ctx->cg_scratch_bytes, sizeof(int) * (size_t)(3 * n + 4));
     if (rc) return rc;
-    int* flag = (int*)ctx->post_scratch;      // n
+    int* flag = (int*)ctx->cg_scratch;        // n
     int* excl = flag + n;                     // n + 1
     int* count = excl + n + 1;                // n (indexed by free rank)
     const int TB = 256;

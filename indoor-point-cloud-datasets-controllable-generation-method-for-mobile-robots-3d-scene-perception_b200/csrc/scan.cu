@@ -792,7 +792,7 @@ extern "C" void lrc_destroy(lrc_ctx* ctx)
     cudaFree(ctx->bvh_block); cudaFree(ctx->labels); cudaFree(ctx->top_table);
     cudaFree(ctx->scratch); cudaFree(ctx->scratch2); cudaFree(ctx->tables); cudaFree(ctx->d_counters);
     cudaFree(ctx->host_dev); cudaFree(ctx->mesh_dev); cudaFree(ctx->post_scratch);
-    cudaFree(ctx->ci_meta); cudaFree(ctx->ci_start); cudaFree(ctx->ci_sorted);
+    cudaFree(ctx->ci_meta); cudaFree(ctx->ci_start); cudaFree(ctx->ci_sorted); cudaFree(ctx->cg_scratch);
     cudaFree(ctx->nn_meta); cudaFree(ctx->nn_start); cudaFree(ctx->nn_sorted);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->scratch_event) cudaEventDestroy(ctx->scratch_event);
