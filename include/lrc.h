@@ -284,7 +284,9 @@ int lrc_kernel_times(lrc_ctx* ctx, double* h_trace_ms, double* h_compact_ms, int
 /* Tuning knobs (defaults are the measured best; none of them changes a result bit):
  *   "variant"       traversal kernel: bit 0 while-while loop, bit 1 256-bit node loads, bit 2 32-register build,
  *                   bit 3 top of the tree in shared memory ("top_levels" 1..8), bit 4 stack in shared memory
- *                   ("stack_levels" 1..48); accepted values 0..3, 5 (default), 13, 21
+ *                   ("stack_levels" 1..48); accepted values 0..3, 1 (default), 5, 13, 21
+ *   "leaf_size"     triangles per leaf built by the NEXT lrc_set_mesh, 1..8 (default 2): subtrees of the radix tree with
+ *                   at most that many Morton-consecutive triangles are tested as one leaf
  *   "node_format"   record format built by the NEXT lrc_set_mesh: 0 = 64 B float boxes (default), 1 = 32 B 16-bit boxes
  *   "block"         threads per traversal block (32 / 64 / 128)
  *   "chunk_rays"    rays per traversal chunk (bounds the 24 B/ray scratch)

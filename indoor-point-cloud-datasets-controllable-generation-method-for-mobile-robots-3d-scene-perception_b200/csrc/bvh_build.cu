@@ -292,7 +292,7 @@ __device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, i
 }
 
 __global__ void k_hierarchy(const uint64_t* __restrict__ keys, int n, int2* __restrict__ children,
-                            int* __restrict__ parent_node, int* __restrict__ parent_leaf)
+                            int* __restrict__ parent_node, int* __restrict__ parent_leaf, int2* __restrict__ range)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
@@ -315,6 +315,7 @@ __global__ void k_hierarchy(const uint64_t* __restrict__ keys, int n, int2* __re
     int left = (lo == gamma) ? ~gamma : gamma;
     int right = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
     children[i] = make_int2(left, right);
+    range[i] = make_int2(lo, hi - lo + 1);          // the Morton-contiguous leaf slots [lo, hi] under this node
     if (left < 0) parent_leaf[~left] = i; else parent_node[left] = i;
     if (right < 0) parent_leaf[~right] = i; else parent_node[right] = i;
     if (i == 0) parent_node[0] = -1;
@@ -373,7 +374,8 @@ __device__ __forceinline__ void write_node_q(float4* __restrict__ rec, const Nod
 
 __global__ void k_refit(int n, const int* __restrict__ parent_leaf, const int* __restrict__ parent_node,
                         const int2* __restrict__ children, const float4* leaf_lo, const float4* leaf_hi, float4* node_lo,
-                        float4* node_hi, int* flags, float4* __restrict__ nodes_out, BuildMeta* meta, int format, NodeQ nq)
+                        float4* node_hi, int* flags, float4* __restrict__ nodes_out, BuildMeta* meta, int format, NodeQ nq,
+                        const int2* __restrict__ range, int leaf_max)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -389,8 +391,13 @@ __global__ void k_refit(int n, const int* __restrict__ parent_leaf, const int* _
         float4 hi = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.f);
         node_lo[cur] = lo;
         node_hi[cur] = hi;
-        if (format == 0) write_node(nodes_out + 4 * (int64_t)cur, l0, h0, l1, h1, ch.x, ch.y);
-        else write_node_q(nodes_out + 2 * (int64_t)cur, nq, l0, h0, l1, h1, ch.x, ch.y);
+        // a child subtree with at most leaf_max triangles becomes ONE leaf over its contiguous slots:
+        // link = ~(first slot | (count - 1) << 28); a single-triangle leaf keeps the plain ~slot form
+        int k0 = ch.x, k1 = ch.y;
+        if (k0 >= 0 && range[k0].y <= leaf_max) k0 = ~(range[k0].x | ((range[k0].y - 1) << 28));
+        if (k1 >= 0 && range[k1].y <= leaf_max) k1 = ~(range[k1].x | ((range[k1].y - 1) << 28));
+        if (format == 0) write_node(nodes_out + 4 * (int64_t)cur, l0, h0, l1, h1, k0, k1);
+        else write_node_q(nodes_out + 2 * (int64_t)cur, nq, l0, h0, l1, h1, k0, k1);
         int up = parent_node[cur];
         if (up < 0) {
             meta->height = (int)height;
@@ -468,7 +475,7 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
                             const uint32_t* tri_label, void* stream_)
 {
     if (!ctx) return lrc_fail(nullptr, LRC_ERR_INVALID, "lrc_set_mesh: ctx is NULL");
-    if (V < 0 || T < 0 || T >= (int64_t)1 << 30) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_mesh: bad V/T (T must be < 2^30)");
+    if (V < 0 || T < 0 || T >= (int64_t)1 << 28) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_mesh: bad V/T (T must be < 2^28)");
     if ((T > 0) && (!verts || !tris)) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_mesh: verts/tris is NULL");
     cudaStream_t stream = (cudaStream_t)stream_;
     LRC_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -513,6 +520,7 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
     size_t o_nlo = carve(sizeof(float4) * n_nodes), o_nhi = carve(sizeof(float4) * n_nodes);
     size_t o_pl = carve(sizeof(int) * T), o_pn = carve(sizeof(int) * n_nodes);
     size_t o_ch = carve(sizeof(int2) * n_nodes), o_fl = carve(sizeof(int) * n_nodes);
+    size_t o_rg = carve(sizeof(int2) * n_nodes);
     int rc = lrc_grow(ctx, &ctx->scratch, &ctx->scratch_bytes, off);
     if (rc) return rc;
     char* base = (char*)ctx->scratch;
@@ -524,6 +532,7 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
     float4* node_lo = (float4*)(base + o_nlo); float4* node_hi = (float4*)(base + o_nhi);
     int* parent_leaf = (int*)(base + o_pl); int* parent_node = (int*)(base + o_pn);
     int2* children = (int2*)(base + o_ch); int* flags = (int*)(base + o_fl);
+    int2* range = (int2*)(base + o_rg);
 
     const int TB = 256;
     const unsigned gT = (unsigned)((T + TB - 1) / TB);
@@ -587,11 +596,11 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
         LRC_CHECK_LAUNCH(ctx, "k_single_leaf_root");
     } else {
         const unsigned gN = (unsigned)((T - 1 + TB - 1) / TB);
-        k_hierarchy<<<gN, TB, 0, stream>>>(kin, (int)T, children, parent_node, parent_leaf);
+        k_hierarchy<<<gN, TB, 0, stream>>>(kin, (int)T, children, parent_node, parent_leaf, range);
         LRC_CHECK_LAUNCH(ctx, "k_hierarchy");
         LRC_CUDA(ctx, cudaMemsetAsync(flags, 0, sizeof(int) * n_nodes, stream));
         k_refit<<<gT, TB, 0, stream>>>((int)T, parent_leaf, parent_node, children, leaf_lo, leaf_hi, node_lo, node_hi, flags,
-                                       ctx->nodes, meta, format, nq);
+                                       ctx->nodes, meta, format, nq, range, (int)ctx->opt_leaf_size);
         LRC_CHECK_LAUNCH(ctx, "k_refit");
     }
     {

@@ -31,6 +31,7 @@ struct lrc_ctx {
     float4* nodes = nullptr;      // num_nodes x 4 float4 (64 B records)
     float4* tris = nullptr;       // T x 3 float4 (48 B records, Morton order): (v0|orig id) (e1|0) (e2|0)
     uint32_t* labels = nullptr;   // T, original triangle order
+    int64_t opt_leaf_size = 2;    // triangles per leaf built by the NEXT lrc_set_mesh (1..8); 2 measured best
     int64_t opt_node_format = 0;  // format the NEXT lrc_set_mesh builds: 0 = 64 B float boxes, 1 = 32 B 16-bit boxes
     int node_format = 0;          // format of the tree that is resident now
     NodeQ nodeq = {};
@@ -118,7 +119,8 @@ struct lrc_ctx {
     // ---- options ----
     int64_t opt_block = 128;            // threads per traversal block
     int64_t opt_chunk_rays = 1 << 26;   // rays per traversal/epilogue chunk (bounds scratch: 16 B per ray)
-    int64_t opt_variant = 5;            // traversal kernel variant: while-while loop, 32-register cap (64 warps per SM)
+    int64_t opt_variant = 1;            // traversal kernel variant: while-while loop (bit 2, the 32-register build, lost
+                                        // its edge once leaves hold two triangles: profiles/r01f_leaf_size_sweep.jsonl)
 };
 
 extern char g_lrc_global_err[512];

@@ -172,7 +172,7 @@ constexpr int TRACE_THREADS = 128;
 // (float4; id = MISS when the ray missed, was dropped or failed the range test), the incident angle, and per BLOCK
 // the number of kept rays (block_count) -- the first stage of the ordered compaction.
 template <int MODE, bool COUNT, bool OUT_DENSE, int VARIANT>
-__global__ void __launch_bounds__(TRACE_THREADS, (VARIANT & 4) ? 16 : 1)   // VARIANT bit 2: cap registers at 32 for 64 warps per SM
+__global__ void __launch_bounds__(TRACE_THREADS, (VARIANT & 4) ? 16 : 12)   // 40 registers (48 warps per SM); VARIANT bit 2: 32 registers (64 warps)
 k_trace(RayGen g, FrameMath fm, const float4* __restrict__ nodes, const float4* __restrict__ tris, int64_t n, int has_tris,
         float4* __restrict__ hp, double* __restrict__ inc_out, unsigned* __restrict__ block_count, float* __restrict__ t_hit,
         uint32_t* __restrict__ prim_id, unsigned long long* counters, const float4* __restrict__ top_table, int top_n,
@@ -870,6 +870,11 @@ extern "C" int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value)
         return LRC_OK;
     }
     if (!strcmp(key, "l2_reset")) { LRC_CUDA(ctx, cudaSetDevice(ctx->device)); LRC_CUDA(ctx, cudaCtxResetPersistingL2Cache()); return LRC_OK; }
+    if (!strcmp(key, "leaf_size")) {
+        if (value < 1 || value > 8) return lrc_fail(ctx, LRC_ERR_INVALID, "leaf_size must be in [1, 8]");
+        ctx->opt_leaf_size = value;        // takes effect at the next lrc_set_mesh
+        return LRC_OK;
+    }
     if (!strcmp(key, "node_format")) {
         if (value != 0 && value != 1) return lrc_fail(ctx, LRC_ERR_INVALID, "node_format must be 0 (64 B float boxes) or 1 (32 B 16-bit boxes)");
         ctx->opt_node_format = value;      // takes effect at the next lrc_set_mesh

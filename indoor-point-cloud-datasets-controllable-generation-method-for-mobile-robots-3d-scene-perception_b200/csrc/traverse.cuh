@@ -100,16 +100,26 @@ __device__ __forceinline__ F8 ldg256(const void* p)
 
 #define LRC_SENTINEL ((int)0x80000000)   // a "leaf" link no tree contains: ~0x80000000 = 0x7fffffff slots
 
+// A leaf link is ~(first slot | (count - 1) << 28): up to 8 Morton-consecutive triangle records (lrc option "leaf_size").
 __device__ __forceinline__ void leaf_test(const float4* __restrict__ tris, int link, float ox, float oy, float oz, float dx,
-                                          float dy, float dz, float& best_t, uint32_t& best_id)
+                                          float dy, float dz, float& best_t, uint32_t& best_id, unsigned& n_tris)
 {
-    const float4* tp = tris + 3 * (int64_t)(~link);
-    const float4 v0 = __ldg(tp + 0), e1 = __ldg(tp + 1), e2 = __ldg(tp + 2);
-    float t;
-    if (mt_hit(ox, oy, oz, dx, dy, dz, v0, e1, e2, t)) {
-        const uint32_t id = __float_as_uint(v0.w);
-        if (t < best_t || (t == best_t && id < best_id)) { best_t = t; best_id = id; }
-    }
+    const unsigned x = ~(unsigned)link;
+    unsigned slot = x & 0x0fffffffu;
+    const unsigned last = slot + (x >> 28);
+    // slot indices (two 32-bit registers) are carried across the intersection test, not pointers -- the kernel is
+    // register-bound; peeling the first triangle out of the loop costs 11 more registers and 3 % (measured)
+#pragma unroll 1
+    do {
+        const float4* tp = tris + 3 * (int64_t)slot;
+        const float4 v0 = __ldg(tp + 0), e1 = __ldg(tp + 1), e2 = __ldg(tp + 2);
+        float t;
+        ++n_tris;
+        if (mt_hit(ox, oy, oz, dx, dy, dz, v0, e1, e2, t)) {
+            const uint32_t id = __float_as_uint(v0.w);
+            if (t < best_t || (t == best_t && id < best_id)) { best_t = t; best_id = id; }
+        }
+    } while (slot++ != last);
 }
 
 // ---- 32-byte nodes: 16-bit boxes on the scene's cell grid (VARIANT bit 5) ----------------------------------------------
@@ -195,7 +205,7 @@ template <> struct StackOps<StackShared> {
 // Top of the tree staged in shared memory (VARIANT bit 3): `s_top` holds the first top_n node records in HEAP order
 // (entry h has its children at 2h+1 / 2h+2), copied there by every block; a link >= LRC_TOP_BASE addresses that table.
 // Records are unmodified copies, so a child link is redirected into the table on the fly when its heap slot exists.
-#define LRC_TOP_BASE 0x40000000   // node ids are < 2^30 (lrc_set_mesh)
+#define LRC_TOP_BASE 0x40000000   // node ids are < 2^28 (lrc_set_mesh)
 
 template <bool COUNT, bool WIDE, bool TOP, class STACK>
 __device__ __forceinline__ int inner_step(const float4* __restrict__ nodes, const float4* s_top, int top_n, int cur,
@@ -284,8 +294,7 @@ __device__ __forceinline__ void trace_loop(const float4* __restrict__ nodes, con
             if (cur >= 0) {
                 cur = inner_step<COUNT, WIDE, TOP>(nodes, s_top, top_n, cur, s, best_t, stack, sp, sm, levels, n_nodes);
             } else {
-                if (COUNT) ++n_tris;
-                leaf_test(tris, cur, ox, oy, oz, dx, dy, dz, best_t, best_id);
+                leaf_test(tris, cur, ox, oy, oz, dx, dy, dz, best_t, best_id, n_tris);
                 cur = StackOps<STACK>::pop(stack, sp, sm, levels);
             }
         }
@@ -293,8 +302,7 @@ __device__ __forceinline__ void trace_loop(const float4* __restrict__ nodes, con
         while (cur != LRC_SENTINEL) {
             while (cur >= 0) cur = inner_step<COUNT, WIDE, TOP>(nodes, s_top, top_n, cur, s, best_t, stack, sp, sm, levels, n_nodes);
             if (cur != LRC_SENTINEL) {
-                if (COUNT) ++n_tris;
-                leaf_test(tris, cur, ox, oy, oz, dx, dy, dz, best_t, best_id);
+                leaf_test(tris, cur, ox, oy, oz, dx, dy, dz, best_t, best_id, n_tris);
                 cur = StackOps<STACK>::pop(stack, sp, sm, levels);
             }
         }
@@ -315,8 +323,7 @@ __device__ __forceinline__ void trace_loop_q(const float4* __restrict__ nodes, c
     while (cur != LRC_SENTINEL) {
         while (cur >= 0) cur = inner_step_q<COUNT>(nodes, cur, s, best_t, stack, sp, nullptr, 0, n_nodes);
         if (cur != LRC_SENTINEL) {
-            if (COUNT) ++n_tris;
-            leaf_test(tris, cur, ox, oy, oz, dx, dy, dz, best_t, best_id);
+            leaf_test(tris, cur, ox, oy, oz, dx, dy, dz, best_t, best_id, n_tris);
             cur = StackOps<StackLocal>::pop(stack, sp, nullptr, 0);
         }
     }

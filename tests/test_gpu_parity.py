@@ -332,9 +332,9 @@ def test_all_traversal_variants_and_block_sizes_give_identical_bits(engine, lrc,
     tiny = lrc.TriangleMesh(np.array([[0, -5, -5], [0, 5, -5], [0, 0, 5.0], [9, -5, -5], [9, 5, -5], [9, 0, 5.0]]) + [4.0, 3, 1], [[0, 1, 2], [3, 4, 5]])
     try:
         for mesh in (c1["mesh"], tiny, lrc.TriangleMesh(tiny.vertices[:3], [[0, 1, 2]])):
-            ctx.set_option("variant", 5); ctx.set_option("block", 128)
+            ctx.set_option("variant", 1); ctx.set_option("block", 128)
             ref = engine.simulate(poses, intr, mesh).numpy()
-            for var, blk, top in ((0, 128, 0), (1, 64, 0), (2, 32, 0), (3, 128, 0), (13, 128, 1), (13, 64, 4), (13, 128, 8),
+            for var, blk, top in ((0, 128, 0), (5, 64, 0), (2, 32, 0), (3, 128, 0), (13, 128, 1), (13, 64, 4), (13, 128, 8),
                                   (21, 128, -1), (21, 64, -3), (21, 128, -40)):
                 ctx.set_option("variant", var); ctx.set_option("block", blk)
                 if top > 0:
@@ -353,5 +353,14 @@ def test_all_traversal_variants_and_block_sizes_give_identical_bits(engine, lrc,
                 ctx.set_option("node_format", 0); ctx._mesh_key = None
             for k in ref:
                 assert np.array_equal(got[k], ref[k]), ("node_format 1", k)
+            # multi-triangle leaves (2, 4, 8 Morton-consecutive triangles per leaf), under both record formats
+            for leaf, fmt in ((1, 0), (4, 0), (8, 0), (1, 1), (4, 1)):
+                ctx.set_option("leaf_size", leaf); ctx.set_option("node_format", fmt); ctx._mesh_key = None
+                try:
+                    got = engine.simulate(poses, intr, mesh).numpy()
+                finally:
+                    ctx.set_option("leaf_size", 2); ctx.set_option("node_format", 0); ctx._mesh_key = None
+                for k in ref:
+                    assert np.array_equal(got[k], ref[k]), ("leaf_size", leaf, fmt, k)
     finally:
-        ctx.set_option("variant", 5); ctx.set_option("block", 128); ctx.set_option("top_levels", 6); ctx.set_option("stack_levels", 12)
+        ctx.set_option("variant", 1); ctx.set_option("block", 128); ctx.set_option("top_levels", 6); ctx.set_option("stack_levels", 12)

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--variants", default="0,1,2,3")
     ap.add_argument("--blocks", default="32,64,128")
     ap.add_argument("--formats", default="0", help="comma list of node formats (0 = 64 B float, 1 = 32 B 16-bit); format 1 ignores --variants")
+    ap.add_argument("--leaf", default="1", help="comma list of leaf sizes (triangles per leaf, rebuilds the tree)")
     ap.add_argument("--l2", default="0", help="comma list of l2_persist percentages")
     ap.add_argument("--stack", default="12", help="comma list of stack_levels for the shared-memory-stack variants (bit 4)")
     ap.add_argument("--top", default="6", help="comma list of top_levels for the shared-memory variants (bit 3)")
@@ -52,13 +53,15 @@ def main():
         for top in ([int(x) for x in args.top.split(",")] if var & 8 else [0]):
             for stk in ([int(x) for x in args.stack.split(",")] if var & 16 else [0]):
                 combos.append((var, l2, top, stk))
-    cur_fmt = 0
-    for var, l2, top, stk in combos:
+    cur_fmt = (0, 1)
+    combos = [c + (lf,) for lf in [int(x) for x in args.leaf.split(",")] for c in combos]
+    for var, l2, top, stk, leaf in combos:
         fmt = 1 if var == 37 else 0
-        if fmt != cur_fmt:
+        if (fmt, leaf) != cur_fmt:
             ctx.set_option("node_format", fmt)
+            ctx.set_option("leaf_size", leaf)
             ctx.set_mesh_arrays(v, f, lab)
-            cur_fmt = fmt
+            cur_fmt = (fmt, leaf)
         if var == 37:
             var_opt = 5
         else:
@@ -85,7 +88,7 @@ def main():
             sig = (m, int(bufs["prim"][:m].to(torch.int64).sum().item()), float(bufs["xyz"][:m].double().sum().item()))
             if ref is None:
                 ref = sig
-            print(json.dumps({"variant": var, "block": blk, "l2_persist": l2, "top_levels": top, "stack_levels": stk, "trace_ms": round(float(np.mean(tr)), 4),
+            print(json.dumps({"variant": var, "block": blk, "l2_persist": l2, "top_levels": top, "stack_levels": stk, "leaf_size": leaf, "trace_ms": round(float(np.mean(tr)), 4),
                               "trace_ms_min": round(float(np.min(tr)), 4), "compact_ms": round(float(np.mean(cp)), 4),
                               "Mrays_s_trace": round(P * n_frame / np.mean(tr) / 1e3, 1), "same_output": sig == ref}), flush=True)
 
