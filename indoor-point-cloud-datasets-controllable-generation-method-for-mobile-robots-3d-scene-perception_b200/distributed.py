@@ -232,12 +232,12 @@ class _RawCudaBuffer:
 
 
 class PeerGather:
-    """Fused compaction + all-gather over NVLink peer memory (``lrc_set_gather``).
+    """All-gather of the compacted clouds over NVLink peer memory (``lrc_set_gather``).
 
     Every rank owns one buffer ``[xyz: world*cap x 3 f32 | label: world*cap u32 | frame_offset: world*(Pmax+1) i64]``
-    allocated by the engine and mapped by all other ranks through CUDA IPC.  While enabled, the compaction kernel of
-    every scan stores rank r's compacted points into region r of ALL buffers (its own and the peers'), chunk by chunk,
-    while the next pose chunk is traversed -- there is no separate collective.  After ``synchronize()`` (stream sync
+    allocated by the engine and mapped by all other ranks through CUDA IPC.  While enabled, every scan pushes rank r's
+    compacted points into region r of ALL buffers (its own and the peers') with the library's exchange kernel (16-byte
+    vector stores), chunk by chunk, while the next pose chunk is traversed -- there is no separate collective.  After ``synchronize()`` (stream sync
     + barrier) each rank holds the whole cloud: frame f of rank r is
     ``xyz[r*cap + off[r, f] - r*cap ...]`` -- see ``views`` / ``assemble_numpy``.
     """
