@@ -368,12 +368,31 @@ class Context:
             nat.check(self._h, self._lib.lrc_scan_single_axis(self._h, _ptr(poses_dev), P, C.byref(d), nzp, C.byref(out), self._stream()))
         return bufs, out
 
-    def scan(self, poses, intr, noise: Optional[NoiseConfig] = None) -> ScanResult:
-        """poses: (P,4,4) float64 (ndarray or tensor).  One fused launch sequence for the whole trajectory."""
+    def scan(self, poses, intr, noise: Optional[NoiseConfig] = None, bufs=None) -> ScanResult:
+        """poses: (P,4,4) float64 (ndarray or tensor).  One fused launch sequence for the whole trajectory.
+        ``bufs`` (from ``_alloc_out``) lets a caller reuse output buffers across calls; the returned tensors are views of
+        them and are overwritten by the next call that uses the same buffers."""
         with torch.cuda.device(self.device):
             p = self._dev(poses, torch.float64).reshape(-1, 16)
-            bufs, _ = self.scan_enqueue(p, intr, noise)
+            bufs, _ = self.scan_enqueue(p, intr, noise, bufs)
             return self._finish(bufs)
+
+    def frame_to_numpy(self, res: "ScanResult"):
+        """(points (m,3) float32, incident (m,) float64) of a one-frame result as fresh numpy arrays: both copies are
+        enqueued into page-locked staging before the single synchronisation."""
+        m = res.num_points
+        if m == 0:
+            return np.zeros((0, 3), np.float32), np.empty(0)
+        st = getattr(self, "_frame_stage", None)
+        if st is None or st[0].shape[0] < m:
+            cap = max(m, 1 << 17)
+            st = (torch.empty((cap, 3), dtype=torch.float32).pin_memory(), torch.empty(cap, dtype=torch.float64).pin_memory())
+            self._frame_stage = st
+        with torch.cuda.device(self.device):
+            st[0][:m].copy_(res.points, non_blocking=True)
+            st[1][:m].copy_(res.incident, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        return st[0][:m].numpy().copy(), st[1][:m].numpy().copy()
 
     # ---- trajectory scan with HOST results: chunked, D2H overlapped with the next chunks' kernels ----
     def alloc_host_buffers(self, capacity: int, frames: int, labels: bool = True, extras: bool = False) -> dict:

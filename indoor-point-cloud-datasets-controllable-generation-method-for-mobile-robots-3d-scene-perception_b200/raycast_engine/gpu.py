@@ -33,6 +33,7 @@ class RaycastEngineGPU(RaycastEngineBase):
         self.cache_mesh = cache_mesh
         self.ctx: Context = get_context(device)
         self.last_scan: Optional[ScanResult] = None
+        self._frame_bufs = None
 
     # ---- reference interface ------------------------------------------------------------------
     def rays_intersect_mesh(self, rays: np.ndarray, mesh):
@@ -51,10 +52,15 @@ class RaycastEngineGPU(RaycastEngineBase):
         """One LiDAR frame: rays -> closest hits -> range filter -> incident angles
         (reference raycast_engine_cpu.py:75-111)."""
         self._prepare(mesh)
-        if isinstance(lidar, IndoorLidar):
-            res = self.ctx.scan(lidar.pose[None], lidar.intrinsics, None)
-        elif isinstance(lidar, DualAxisLidar):
-            res = self.ctx.scan(lidar.pose[None], lidar.intrinsics, lidar.noise_config())
+        if isinstance(lidar, (IndoorLidar, DualAxisLidar)):
+            # one frame per call is the reference's call pattern: the output buffers are kept per sensor size, so
+            # ``last_scan`` stays valid until the next call
+            from ..core import rays_per_frame
+            n = rays_per_frame(lidar.intrinsics)
+            if self._frame_bufs is None or self._frame_bufs[0] != n:
+                self._frame_bufs = (n, self.ctx._alloc_out(n, 1)[0])
+            noise = lidar.noise_config() if isinstance(lidar, DualAxisLidar) else None
+            res = self.ctx.scan(lidar.pose[None], lidar.intrinsics, noise, bufs=self._frame_bufs[1])
         else:
             # duck-typed sensor (the reference touches only get_rays(), pose[:3,3], intrinsics.max_range)
             rays = lidar.get_rays()
@@ -65,9 +71,7 @@ class RaycastEngineGPU(RaycastEngineBase):
             res = self.ctx.scan_rays(rays.astype(np.float32), np.asarray(lidar.pose, dtype=np.float64)[:3, 3],
                                      float(lidar.intrinsics.max_range))
         self.last_scan = res
-        points = res.points.cpu().numpy()
-        incident = res.incident.cpu().numpy() if len(points) > 0 else np.empty(0)   # reference :109
-        return points, incident
+        return self.ctx.frame_to_numpy(res)                                          # empty frame -> np.empty(0), reference :109
 
     # ---- extensions ---------------------------------------------------------------------------
     def _prepare(self, mesh) -> None:
