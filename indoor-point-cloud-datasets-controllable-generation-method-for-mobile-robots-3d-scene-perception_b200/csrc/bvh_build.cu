@@ -30,6 +30,7 @@ struct BuildMeta {            // lives in device memory during a build
     int bad_index;            // set when a triangle references a vertex outside [0, V)
     int height;               // tree height (edges on the longest root->leaf path)
     float root_lo[3], root_hi[3];
+    int root;                 // index of the root's node record (0 for the radix tree; in-order index for PLOC)
 };
 
 __global__ void k_meta_init(BuildMeta* m)
@@ -37,6 +38,7 @@ __global__ void k_meta_init(BuildMeta* m)
     for (int k = 0; k < 3; ++k) { m->lo[k] = 0xffffffffu; m->hi[k] = 0u; }
     m->bad_index = 0;
     m->height = 0;
+    m->root = 0;
 }
 
 // scene AABB over the vertex array (coalesced; a vertex no triangle references still counts -- harmless for the
@@ -261,7 +263,7 @@ k_rs_scatter(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ 
 __global__ void k_leaf_init(const float* __restrict__ verts, const int32_t* __restrict__ tris, int64_t T,
                             const uint32_t* __restrict__ sorted_ids, float pad, float4* __restrict__ tri_rec,
                             float4* __restrict__ leaf_lo, float4* __restrict__ leaf_hi)
-{
+{   // tri_rec == nullptr: boxes only (the PLOC builder writes the records later, in depth-first leaf order)
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= T) return;
     uint32_t id = sorted_ids[i];
@@ -273,9 +275,11 @@ __global__ void k_leaf_init(const float* __restrict__ verts, const int32_t* __re
         c[k] = verts[3 * (int64_t)tris[3 * (int64_t)id + 2] + k];
     }
     // e1 = v1 - v0, e2 = v2 - v0: one IEEE subtraction each -- part of the intersection spec
-    tri_rec[3 * i + 0] = make_float4(a[0], a[1], a[2], __uint_as_float(id));
-    tri_rec[3 * i + 1] = make_float4(__fsub_rn(b[0], a[0]), __fsub_rn(b[1], a[1]), __fsub_rn(b[2], a[2]), 0.f);
-    tri_rec[3 * i + 2] = make_float4(__fsub_rn(c[0], a[0]), __fsub_rn(c[1], a[1]), __fsub_rn(c[2], a[2]), 0.f);
+    if (tri_rec) {
+        tri_rec[3 * i + 0] = make_float4(a[0], a[1], a[2], __uint_as_float(id));
+        tri_rec[3 * i + 1] = make_float4(__fsub_rn(b[0], a[0]), __fsub_rn(b[1], a[1]), __fsub_rn(b[2], a[2]), 0.f);
+        tri_rec[3 * i + 2] = make_float4(__fsub_rn(c[0], a[0]), __fsub_rn(c[1], a[1]), __fsub_rn(c[2], a[2]), 0.f);
+    }
     leaf_lo[i] = make_float4(fminf(a[0], fminf(b[0], c[0])) - pad, fminf(a[1], fminf(b[1], c[1])) - pad,
                              fminf(a[2], fminf(b[2], c[2])) - pad, 0.f);
     leaf_hi[i] = make_float4(fmaxf(a[0], fmaxf(b[0], c[0])) + pad, fmaxf(a[1], fmaxf(b[1], c[1])) + pad,
@@ -423,10 +427,10 @@ __global__ void k_single_leaf_root(const float4* leaf_lo, const float4* leaf_hi,
 
 // Heap-ordered copy of the top K node records (entry h: children at 2h+1, 2h+2) for the traversal variant that stages
 // the top of the tree in shared memory.  One block; levels are resolved one after the other.
-__global__ void __launch_bounds__(256) k_top_table(const float4* __restrict__ nodes, float4* __restrict__ top, int K)
+__global__ void __launch_bounds__(256) k_top_table(const float4* __restrict__ nodes, float4* __restrict__ top, int K, int root)
 {
     __shared__ int gid[256];
-    for (int h = threadIdx.x; h < 256; h += blockDim.x) gid[h] = h == 0 ? 0 : -1;
+    for (int h = threadIdx.x; h < 256; h += blockDim.x) gid[h] = h == 0 ? root : -1;
     __syncthreads();
     for (int s = 1; s < K; s = 2 * s + 1) {                 // level [s, 2s+1)
         for (int h = s + threadIdx.x; h < min(2 * s + 1, K); h += blockDim.x) {
@@ -470,6 +474,8 @@ __global__ void k_sah_sum(const float4* __restrict__ nodes, int64_t n_nodes, dou
 
 }  // namespace
 
+#include "bvh_ploc.cuh"
+
 // -------------------------------------------------------------------------------------------------
 extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const int32_t* tris, int64_t T,
                             const uint32_t* tri_label, void* stream_)
@@ -508,6 +514,11 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
     if (tri_label) LRC_CUDA(ctx, cudaMemcpyAsync(ctx->labels, tri_label, sizeof(uint32_t) * T, cudaMemcpyDeviceToDevice, stream));
     else LRC_CUDA(ctx, cudaMemsetAsync(ctx->labels, 0, sizeof(uint32_t) * T, stream));
 
+    // the build scratch is carved out of ctx->scratch, which scans use as well: order this build after the last scan,
+    // whatever stream that ran on
+    if (ctx->scratch_event) LRC_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->scratch_event, 0));
+    const int quality = (T > 2) ? (int)ctx->opt_build_quality : 0;
+
     // ---- carve the build scratch ----
     const int nb = (int)((T + RS_TILE - 1) / RS_TILE);
     size_t off = 0;
@@ -521,6 +532,17 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
     size_t o_pl = carve(sizeof(int) * T), o_pn = carve(sizeof(int) * n_nodes);
     size_t o_ch = carve(sizeof(int2) * n_nodes), o_fl = carve(sizeof(int) * n_nodes);
     size_t o_rg = carve(sizeof(int2) * n_nodes);
+    // PLOC only: two cluster buffers, per-iteration bookkeeping, subtree positions (o_ch / o_rg hold left|right and
+    // left-count|start; the key buffer k1 is free after the sort)
+    size_t o_cid0 = 0, o_cid1 = 0, o_clo0 = 0, o_clo1 = 0, o_chi0 = 0, o_chi1 = 0, o_nn = 0, o_role = 0, o_bsum = 0, o_sl = 0;
+    if (quality) {
+        o_cid0 = carve(sizeof(int) * T); o_cid1 = carve(sizeof(int) * T);
+        o_clo0 = carve(sizeof(float4) * T); o_clo1 = carve(sizeof(float4) * T);
+        o_chi0 = carve(sizeof(float4) * T); o_chi1 = carve(sizeof(float4) * T);
+        o_nn = carve(sizeof(int) * T); o_role = carve((size_t)T);
+        o_bsum = carve(sizeof(uint2) * (size_t)((T + PL_THREADS - 1) / PL_THREADS));
+        o_sl = carve(sizeof(int) * T);
+    }
     int rc = lrc_grow(ctx, &ctx->scratch, &ctx->scratch_bytes, off);
     if (rc) return rc;
     char* base = (char*)ctx->scratch;
@@ -589,30 +611,66 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
         uint32_t* tv = vin; vin = vout; vout = tv;
     }
     // after an even number of passes the sorted data is back in (k0, v0) == (kin, vin)
-    k_leaf_init<<<gT, TB, 0, stream>>>(verts, tris, T, vin, pad, ctx->tris, leaf_lo, leaf_hi);
-    LRC_CHECK_LAUNCH(ctx, "k_leaf_init");
-    if (T == 1) {
-        k_single_leaf_root<<<1, 1, 0, stream>>>(leaf_lo, leaf_hi, ctx->nodes, meta, format, nq);
-        LRC_CHECK_LAUNCH(ctx, "k_single_leaf_root");
+    int ploc_iters = 0;
+    if (quality) {
+        // ---- SAH-quality build: PLOC over the Morton-ordered leaves (bvh_ploc.cuh) ----
+        k_leaf_init<<<gT, TB, 0, stream>>>(verts, tris, T, vin, pad, nullptr, leaf_lo, leaf_hi);
+        LRC_CHECK_LAUNCH(ctx, "k_leaf_init");
+        if (!ctx->h_pin) LRC_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_pin, sizeof(int) * 16, cudaHostAllocDefault));
+        int* cid[2] = {(int*)(base + o_cid0), (int*)(base + o_cid1)};
+        float4* clo[2] = {(float4*)(base + o_clo0), (float4*)(base + o_clo1)};
+        float4* chi[2] = {(float4*)(base + o_chi0), (float4*)(base + o_chi1)};
+        PlocTree tr;
+        tr.left = (int*)children; tr.right = tr.left + n_nodes;
+        tr.cl = (int*)range; tr.start_node = tr.cl + n_nodes;
+        tr.lo = node_lo; tr.hi = node_hi;
+        tr.parent_node = parent_node; tr.parent_leaf = parent_leaf;
+        tr.start_leaf = (int*)(base + o_sl);
+        k_ploc_init<<<gT, TB, 0, stream>>>((int)T, leaf_lo, leaf_hi, cid[0], clo[0], chi[0]);
+        LRC_CHECK_LAUNCH(ctx, "k_ploc_init");
+        int R = (int)ctx->opt_ploc_radius;
+        if ((rc = ploc_build(ctx, (int)T, R, cid, clo, chi, (int*)(base + o_nn), (unsigned char*)(base + o_role), (uint2*)(base + o_bsum),
+                             tr, ctx->h_pin, &ploc_iters, stream))) return rc;
+        LRC_CUDA(ctx, cudaMemsetAsync(parent_node + (T - 2), 0xff, sizeof(int), stream));      // the root (last node created) has no parent
+        k_ploc_positions<<<(unsigned)((2 * T - 1 + TB - 1) / TB), TB, 0, stream>>>((int)T, tr, meta);
+        LRC_CHECK_LAUNCH(ctx, "k_ploc_positions");
+        k_ploc_emit<<<(unsigned)((T - 1 + TB - 1) / TB), TB, 0, stream>>>((int)T, tr, leaf_lo, leaf_hi, ctx->nodes, format, nq,
+                                                                          (int)ctx->opt_leaf_size, meta);
+        LRC_CHECK_LAUNCH(ctx, "k_ploc_emit");
+        k_tri_records<<<gT, TB, 0, stream>>>(verts, tris, T, vin, tr.start_leaf, ctx->tris);
+        LRC_CHECK_LAUNCH(ctx, "k_tri_records");
     } else {
-        const unsigned gN = (unsigned)((T - 1 + TB - 1) / TB);
-        k_hierarchy<<<gN, TB, 0, stream>>>(kin, (int)T, children, parent_node, parent_leaf, range);
-        LRC_CHECK_LAUNCH(ctx, "k_hierarchy");
-        LRC_CUDA(ctx, cudaMemsetAsync(flags, 0, sizeof(int) * n_nodes, stream));
-        k_refit<<<gT, TB, 0, stream>>>((int)T, parent_leaf, parent_node, children, leaf_lo, leaf_hi, node_lo, node_hi, flags,
-                                       ctx->nodes, meta, format, nq, range, (int)ctx->opt_leaf_size);
-        LRC_CHECK_LAUNCH(ctx, "k_refit");
-    }
-    {
-        const int K = (1 << LRC_TOP_LEVELS_MAX) - 1;
-        if (!ctx->top_table) LRC_CUDA(ctx, cudaMalloc((void**)&ctx->top_table, sizeof(float4) * 4 * K));
-        if (format == 0) {      // the shared-memory top-of-tree variant exists for the float format only
-            k_top_table<<<1, 256, 0, stream>>>(ctx->nodes, ctx->top_table, K);
-            LRC_CHECK_LAUNCH(ctx, "k_top_table");
+        k_leaf_init<<<gT, TB, 0, stream>>>(verts, tris, T, vin, pad, ctx->tris, leaf_lo, leaf_hi);
+        LRC_CHECK_LAUNCH(ctx, "k_leaf_init");
+        if (T == 1) {
+            k_single_leaf_root<<<1, 1, 0, stream>>>(leaf_lo, leaf_hi, ctx->nodes, meta, format, nq);
+            LRC_CHECK_LAUNCH(ctx, "k_single_leaf_root");
+        } else {
+            const unsigned gN = (unsigned)((T - 1 + TB - 1) / TB);
+            k_hierarchy<<<gN, TB, 0, stream>>>(kin, (int)T, children, parent_node, parent_leaf, range);
+            LRC_CHECK_LAUNCH(ctx, "k_hierarchy");
+            LRC_CUDA(ctx, cudaMemsetAsync(flags, 0, sizeof(int) * n_nodes, stream));
+            k_refit<<<gT, TB, 0, stream>>>((int)T, parent_leaf, parent_node, children, leaf_lo, leaf_hi, node_lo, node_hi, flags,
+                                           ctx->nodes, meta, format, nq, range, (int)ctx->opt_leaf_size);
+            LRC_CHECK_LAUNCH(ctx, "k_refit");
         }
     }
     LRC_CUDA(ctx, cudaMemcpyAsync(&hm, meta, sizeof hm, cudaMemcpyDeviceToHost, stream));
     LRC_CUDA(ctx, cudaStreamSynchronize(stream));
+    ctx->root = hm.root;
+    ctx->build_quality = quality;
+    ctx->ploc_iterations = ploc_iters;
+    {
+        const int K = (1 << LRC_TOP_LEVELS_MAX) - 1;
+        if (!ctx->top_table) LRC_CUDA(ctx, cudaMalloc((void**)&ctx->top_table, sizeof(float4) * 4 * K));
+        if (format == 0) {      // the shared-memory top-of-tree variant exists for the float format only
+            k_top_table<<<1, 256, 0, stream>>>(ctx->nodes, ctx->top_table, K, ctx->root);
+            LRC_CHECK_LAUNCH(ctx, "k_top_table");
+        }
+    }
+    // scans that follow on other streams must see the finished tree; the scratch is theirs again after this point
+    if (!ctx->scratch_event) LRC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->scratch_event, cudaEventDisableTiming));
+    LRC_CUDA(ctx, cudaEventRecord(ctx->scratch_event, stream));
 
     lrc_bvh_info& inf = ctx->info;
     inf.num_tris = T;
@@ -627,6 +685,14 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
     }
     inf.bytes_nodes = (int64_t)sizeof(float4) * (format == 0 ? 4 : 2) * n_nodes;
     inf.bytes_tris = (int64_t)sizeof(float4) * 3 * T;
+    if (hm.height + 1 >= LRC_STACK_DEPTH && quality) {
+        // a PLOC tree has no height bound; the radix tree's is the key length -- rebuild with it rather than fail
+        const int64_t keep = ctx->opt_build_quality;
+        ctx->opt_build_quality = 0;
+        rc = lrc_set_mesh(ctx, verts, V, tris, T, tri_label, stream_);
+        ctx->opt_build_quality = keep;
+        return rc;
+    }
     if (hm.height + 1 >= LRC_STACK_DEPTH) {
         char buf[32];
         snprintf(buf, sizeof buf, "%d", hm.height);

@@ -32,6 +32,12 @@ struct lrc_ctx {
     float4* tris = nullptr;       // T x 3 float4 (48 B records, Morton order): (v0|orig id) (e1|0) (e2|0)
     uint32_t* labels = nullptr;   // T, original triangle order
     int64_t opt_leaf_size = 2;    // triangles per leaf built by the NEXT lrc_set_mesh (1..8); 2 measured best
+    int64_t opt_build_quality = 1;   // builder of the NEXT lrc_set_mesh: 0 = LBVH (Karras radix tree), 1 = PLOC (bvh_ploc.cuh)
+    int64_t opt_ploc_radius = 16;    // PLOC search radius (clusters before / after in Morton order), 1..32
+    int build_quality = 0;        // builder of the tree that is resident now
+    int ploc_iterations = 0;
+    int root = 0;                 // node record the traversal starts at
+    int* h_pin = nullptr;         // small page-locked mailbox (PLOC merge counts)
     int64_t opt_node_format = 0;  // format the NEXT lrc_set_mesh builds: 0 = 64 B float boxes, 1 = 32 B 16-bit boxes
     int node_format = 0;          // format of the tree that is resident now
     NodeQ nodeq = {};

@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, (VARIANT & 4) ? 16 : 12)   // 4
 k_trace(RayGen g, FrameMath fm, const float4* __restrict__ nodes, const float4* __restrict__ tris, int64_t n, int has_tris,
         float4* __restrict__ hp, double* __restrict__ inc_out, unsigned* __restrict__ block_count, float* __restrict__ t_hit,
         uint32_t* __restrict__ prim_id, unsigned long long* counters, const float4* __restrict__ top_table, int top_n,
-        int stack_levels, const __grid_constant__ NodeQ nq)
+        int stack_levels, const __grid_constant__ NodeQ nq, int root)
 {
     extern __shared__ float4 s_top[];
     if (VARIANT & 8) {      // stage the top of the tree (heap order, built by lrc_set_mesh) in shared memory
@@ -192,7 +192,7 @@ k_trace(RayGen g, FrameMath fm, const float4* __restrict__ nodes, const float4* 
         float t = LRC_INF;
         uint32_t id = LRC_MISS_ID;
         if (ray.keep && has_tris) {
-            trace_ray<VARIANT, COUNT>(nodes, tris, s_top, top_n, stack_levels, nq, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, t, id, nn, nt);
+            trace_ray<VARIANT, COUNT>(nodes, tris, s_top, top_n, stack_levels, nq, root, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, t, id, nn, nt);
             nr = 1;
             nh = id != LRC_MISS_ID;
         }
@@ -509,6 +509,7 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
     unsigned long long* counters = ctx->d_counters;
     const float4* top_table = ctx->top_table;
     const NodeQ nq = ctx->nodeq;
+    const int root = ctx->root;
     // the resident tree's record format selects the kernel family; the variant option tunes the float-format kernels
     const int64_t variant = ctx->node_format == 1 ? 37 : ctx->opt_variant;
     const int top_n = (variant & 8) ? (int)((1 << ctx->opt_top_levels) - 1) : 0;
@@ -516,7 +517,7 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
     cfg.dynamicSmemBytes = (variant & 16) ? (size_t)stack_levels * LRC_SS_STRIDE * sizeof(int) : (size_t)top_n * 64;
     cudaError_t le = cudaSuccess;
 #define LRC_LAUNCH_TRACE(COUNT, VARIANT) \
-    le = cudaLaunchKernelEx(&cfg, k_trace<MODE, COUNT, DENSE, VARIANT>, g, fm, nodes, tris, n, has_tris, hp, inc, block_count, t_hit, prim, counters, top_table, top_n, stack_levels, nq)
+    le = cudaLaunchKernelEx(&cfg, k_trace<MODE, COUNT, DENSE, VARIANT>, g, fm, nodes, tris, n, has_tris, hp, inc, block_count, t_hit, prim, counters, top_table, top_n, stack_levels, nq, root)
     if (ctx->counting) {
         switch (variant) {
             case 0: LRC_LAUNCH_TRACE(true, 0); break;
@@ -526,6 +527,7 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
             case 13: LRC_LAUNCH_TRACE(true, 13); break;
             case 21: LRC_LAUNCH_TRACE(true, 21); break;
             case 37: LRC_LAUNCH_TRACE(true, 37); break;
+            case 65: LRC_LAUNCH_TRACE(true, 65); break;
             default: LRC_LAUNCH_TRACE(true, 3); break;
         }
     } else {
@@ -537,6 +539,7 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
             case 13: LRC_LAUNCH_TRACE(false, 13); break;
             case 21: LRC_LAUNCH_TRACE(false, 21); break;
             case 37: LRC_LAUNCH_TRACE(false, 37); break;
+            case 65: LRC_LAUNCH_TRACE(false, 65); break;
             default: LRC_LAUNCH_TRACE(false, 3); break;
         }
     }
@@ -795,6 +798,7 @@ extern "C" void lrc_destroy(lrc_ctx* ctx)
     cudaFree(ctx->ci_meta); cudaFree(ctx->ci_start); cudaFree(ctx->ci_sorted); cudaFree(ctx->cg_scratch);
     cudaFree(ctx->nn_meta); cudaFree(ctx->nn_start); cudaFree(ctx->nn_sorted);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->scratch_event) cudaEventDestroy(ctx->scratch_event);
     for (cudaEvent_t e : ctx->kt_events) cudaEventDestroy(e);
     if (ctx->s_aux) { cudaStreamDestroy(ctx->s_aux); for (int k = 0; k < 4; ++k) cudaEventDestroy(ctx->pipe_ev[k]); }
@@ -875,6 +879,16 @@ extern "C" int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value)
         ctx->opt_leaf_size = value;        // takes effect at the next lrc_set_mesh
         return LRC_OK;
     }
+    if (!strcmp(key, "build_quality")) {
+        if (value != 0 && value != 1) return lrc_fail(ctx, LRC_ERR_INVALID, "build_quality must be 0 (LBVH) or 1 (PLOC)");
+        ctx->opt_build_quality = value;    // takes effect at the next lrc_set_mesh
+        return LRC_OK;
+    }
+    if (!strcmp(key, "ploc_radius")) {
+        if (value < 1 || value > 32) return lrc_fail(ctx, LRC_ERR_INVALID, "ploc_radius must be in [1, 32]");
+        ctx->opt_ploc_radius = value;
+        return LRC_OK;
+    }
     if (!strcmp(key, "node_format")) {
         if (value != 0 && value != 1) return lrc_fail(ctx, LRC_ERR_INVALID, "node_format must be 0 (64 B float boxes) or 1 (32 B 16-bit boxes)");
         ctx->opt_node_format = value;      // takes effect at the next lrc_set_mesh
@@ -900,7 +914,7 @@ extern "C" int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value)
     }
     if (!strcmp(key, "kernel_timing")) { ctx->opt_kernel_timing = value != 0; ctx->kt_used = 0; return LRC_OK; }
     if (!strcmp(key, "variant")) {
-        if (value < 0 || (value > 3 && value != 5 && value != 13 && value != 21)) return lrc_fail(ctx, LRC_ERR_INVALID, "variant must be 0..3, 5, 13 or 21");
+        if (value < 0 || (value > 3 && value != 5 && value != 13 && value != 21 && value != 65)) return lrc_fail(ctx, LRC_ERR_INVALID, "variant must be 0..3, 5, 13, 21 or 65");
         ctx->opt_variant = value;
         return LRC_OK;
     }

@@ -180,6 +180,21 @@ struct StackLocal {
     __device__ __forceinline__ void push(int& sp, int v) { a[sp++] = v; }
     __device__ __forceinline__ int pop(int& sp) { return sp > 0 ? a[--sp] : LRC_SENTINEL; }
 };
+// StackCull (VARIANT bit 6): every entry carries the distance at which the ray enters that child's box; an entry whose
+// distance already exceeds the best hit is dropped at pop time without fetching its node record.
+struct StackCull {
+    int a[LRC_STACK_DEPTH];
+    float t[LRC_STACK_DEPTH];
+    __device__ __forceinline__ void push(int& sp, int v, float tn) { a[sp] = v; t[sp] = tn; ++sp; }
+    __device__ __forceinline__ int pop(int& sp, float best_t)
+    {
+        while (sp > 0) {
+            --sp;
+            if (t[sp] <= best_t) return a[sp];
+        }
+        return LRC_SENTINEL;
+    }
+};
 struct StackShared {
     int a[LRC_STACK_DEPTH];
     __device__ __forceinline__ void push(int& sp, int v, int* sm, int levels) { if (sp < levels) sm[sp * LRC_SS_STRIDE] = v; else a[sp - levels] = v; ++sp; }
@@ -193,12 +208,16 @@ struct StackShared {
 // uniform access for both policies: sm / levels are ignored by the local stack
 template <class STACK> struct StackOps;
 template <> struct StackOps<StackLocal> {
-    static __device__ __forceinline__ void push(StackLocal& st, int& sp, int v, int*, int) { st.push(sp, v); }
-    static __device__ __forceinline__ int pop(StackLocal& st, int& sp, int*, int) { return st.pop(sp); }
+    static __device__ __forceinline__ void push(StackLocal& st, int& sp, int v, float, int*, int) { st.push(sp, v); }
+    static __device__ __forceinline__ int pop(StackLocal& st, int& sp, float, int*, int) { return st.pop(sp); }
+};
+template <> struct StackOps<StackCull> {
+    static __device__ __forceinline__ void push(StackCull& st, int& sp, int v, float tn, int*, int) { st.push(sp, v, tn); }
+    static __device__ __forceinline__ int pop(StackCull& st, int& sp, float best_t, int*, int) { return st.pop(sp, best_t); }
 };
 template <> struct StackOps<StackShared> {
-    static __device__ __forceinline__ void push(StackShared& st, int& sp, int v, int* sm, int levels) { st.push(sp, v, sm, levels); }
-    static __device__ __forceinline__ int pop(StackShared& st, int& sp, int* sm, int levels) { return st.pop(sp, sm, levels); }
+    static __device__ __forceinline__ void push(StackShared& st, int& sp, int v, float, int* sm, int levels) { st.push(sp, v, sm, levels); }
+    static __device__ __forceinline__ int pop(StackShared& st, int& sp, float, int* sm, int levels) { return st.pop(sp, sm, levels); }
 };
 
 // One step at an inner node: returns the next link (child to descend into, or a popped entry, or the sentinel).
@@ -241,12 +260,12 @@ __device__ __forceinline__ int inner_step(const float4* __restrict__ nodes, cons
     const bool h1 = slab_ch(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, s, best_t, t1);
     if (h0 && h1) {
         const bool swp = t1 < t0;              // nearer child first, farther one on the stack
-        StackOps<STACK>::push(stack, sp, swp ? l0 : l1, sm, levels);
+        StackOps<STACK>::push(stack, sp, swp ? l0 : l1, swp ? t0 : t1, sm, levels);
         return swp ? l1 : l0;
     }
     if (h0) return l0;
     if (h1) return l1;
-    return StackOps<STACK>::pop(stack, sp, sm, levels);
+    return StackOps<STACK>::pop(stack, sp, best_t, sm, levels);
 }
 
 template <bool COUNT, class STACK>
@@ -262,12 +281,12 @@ __device__ __forceinline__ int inner_step_q(const float4* __restrict__ nodes, in
     const int l0 = (int)a.w, l1 = (int)b.w;
     if (h0 && h1) {
         const bool swp = t1 < t0;
-        StackOps<STACK>::push(stack, sp, swp ? l0 : l1, sm, levels);
+        StackOps<STACK>::push(stack, sp, swp ? l0 : l1, swp ? t0 : t1, sm, levels);
         return swp ? l1 : l0;
     }
     if (h0) return l0;
     if (h1) return l1;
-    return StackOps<STACK>::pop(stack, sp, sm, levels);
+    return StackOps<STACK>::pop(stack, sp, best_t, sm, levels);
 }
 
 // Stack-based closest-hit traversal.  VARIANT bit 0: 0 = one node (inner or leaf) per loop trip ("if-if"),
@@ -276,9 +295,10 @@ __device__ __forceinline__ int inner_step_q(const float4* __restrict__ nodes, in
 // VARIANT bit 3: the first top_n nodes (heap order) are read from shared memory.
 // VARIANT bit 4: the first stack levels live in shared memory (StackShared).
 // VARIANT bit 5: 32-byte quantised node records (trace_loop_q; while-while only).
+// VARIANT bit 6: stack entries carry their entry distance and are culled against the best hit at pop time (StackCull).
 template <int VARIANT, bool COUNT, class STACK>
 __device__ __forceinline__ void trace_loop(const float4* __restrict__ nodes, const float4* __restrict__ tris,
-                                           const float4* s_top, int top_n, STACK& stack, int* sm, int levels, float ox,
+                                           const float4* s_top, int top_n, int root, STACK& stack, int* sm, int levels, float ox,
                                            float oy, float oz, float dx, float dy, float dz, float& best_t,
                                            uint32_t& best_id, unsigned& n_nodes, unsigned& n_tris)
 {
@@ -288,14 +308,14 @@ __device__ __forceinline__ void trace_loop(const float4* __restrict__ nodes, con
     int sp = 0;
     constexpr bool WIDE = (VARIANT & 2) != 0;
     constexpr bool TOP = (VARIANT & 8) != 0;
-    int cur = (TOP && top_n > 0) ? LRC_TOP_BASE : 0;
+    int cur = (TOP && top_n > 0) ? LRC_TOP_BASE : root;
     if ((VARIANT & 1) == 0) {
         while (cur != LRC_SENTINEL) {
             if (cur >= 0) {
                 cur = inner_step<COUNT, WIDE, TOP>(nodes, s_top, top_n, cur, s, best_t, stack, sp, sm, levels, n_nodes);
             } else {
                 leaf_test(tris, cur, ox, oy, oz, dx, dy, dz, best_t, best_id, n_tris);
-                cur = StackOps<STACK>::pop(stack, sp, sm, levels);
+                cur = StackOps<STACK>::pop(stack, sp, best_t, sm, levels);
             }
         }
     } else {
@@ -303,7 +323,7 @@ __device__ __forceinline__ void trace_loop(const float4* __restrict__ nodes, con
             while (cur >= 0) cur = inner_step<COUNT, WIDE, TOP>(nodes, s_top, top_n, cur, s, best_t, stack, sp, sm, levels, n_nodes);
             if (cur != LRC_SENTINEL) {
                 leaf_test(tris, cur, ox, oy, oz, dx, dy, dz, best_t, best_id, n_tris);
-                cur = StackOps<STACK>::pop(stack, sp, sm, levels);
+                cur = StackOps<STACK>::pop(stack, sp, best_t, sm, levels);
             }
         }
     }
@@ -311,7 +331,7 @@ __device__ __forceinline__ void trace_loop(const float4* __restrict__ nodes, con
 
 template <bool COUNT>
 __device__ __forceinline__ void trace_loop_q(const float4* __restrict__ nodes, const float4* __restrict__ tris, const NodeQ& nq,
-                                             float ox, float oy, float oz, float dx, float dy, float dz, float& best_t,
+                                             int root, float ox, float oy, float oz, float dx, float dy, float dz, float& best_t,
                                              uint32_t& best_id, unsigned& n_nodes, unsigned& n_tris)
 {
     best_t = LRC_INF;
@@ -319,12 +339,12 @@ __device__ __forceinline__ void trace_loop_q(const float4* __restrict__ nodes, c
     const RaySlabQ s = make_slab_q(ox, oy, oz, dx, dy, dz, nq);
     StackLocal stack;
     int sp = 0;
-    int cur = 0;
+    int cur = root;
     while (cur != LRC_SENTINEL) {
         while (cur >= 0) cur = inner_step_q<COUNT>(nodes, cur, s, best_t, stack, sp, nullptr, 0, n_nodes);
         if (cur != LRC_SENTINEL) {
             leaf_test(tris, cur, ox, oy, oz, dx, dy, dz, best_t, best_id, n_tris);
-            cur = StackOps<StackLocal>::pop(stack, sp, nullptr, 0);
+            cur = StackOps<StackLocal>::pop(stack, sp, best_t, nullptr, 0);
         }
     }
 }
@@ -332,18 +352,21 @@ __device__ __forceinline__ void trace_loop_q(const float4* __restrict__ nodes, c
 // `smem` = the block's dynamic shared memory: the heap-ordered top table (bit 3) or the shared stack levels (bit 4).
 template <int VARIANT, bool COUNT>
 __device__ __forceinline__ void trace_ray(const float4* __restrict__ nodes, const float4* __restrict__ tris,
-                                          const float4* smem, int top_n, int stack_levels, const NodeQ& nq, float ox,
+                                          const float4* smem, int top_n, int stack_levels, const NodeQ& nq, int root, float ox,
                                           float oy, float oz, float dx, float dy, float dz, float& best_t,
                                           uint32_t& best_id, unsigned& n_nodes, unsigned& n_tris)
 {
     if (VARIANT & 32) {
-        trace_loop_q<COUNT>(nodes, tris, nq, ox, oy, oz, dx, dy, dz, best_t, best_id, n_nodes, n_tris);
+        trace_loop_q<COUNT>(nodes, tris, nq, root, ox, oy, oz, dx, dy, dz, best_t, best_id, n_nodes, n_tris);
     } else if (VARIANT & 16) {
         StackShared st;
         int* sm = reinterpret_cast<int*>(const_cast<float4*>(smem)) + threadIdx.x;   // this thread's column of the shared table
-        trace_loop<VARIANT, COUNT>(nodes, tris, smem, top_n, st, sm, stack_levels, ox, oy, oz, dx, dy, dz, best_t, best_id, n_nodes, n_tris);
+        trace_loop<VARIANT, COUNT>(nodes, tris, smem, top_n, root, st, sm, stack_levels, ox, oy, oz, dx, dy, dz, best_t, best_id, n_nodes, n_tris);
+    } else if (VARIANT & 64) {
+        StackCull st;
+        trace_loop<VARIANT, COUNT>(nodes, tris, smem, top_n, root, st, nullptr, 0, ox, oy, oz, dx, dy, dz, best_t, best_id, n_nodes, n_tris);
     } else {
         StackLocal st;
-        trace_loop<VARIANT, COUNT>(nodes, tris, smem, top_n, st, nullptr, 0, ox, oy, oz, dx, dy, dz, best_t, best_id, n_nodes, n_tris);
+        trace_loop<VARIANT, COUNT>(nodes, tris, smem, top_n, root, st, nullptr, 0, ox, oy, oz, dx, dy, dz, best_t, best_id, n_nodes, n_tris);
     }
 }
