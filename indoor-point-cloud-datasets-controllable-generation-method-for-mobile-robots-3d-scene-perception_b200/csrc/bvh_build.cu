@@ -356,6 +356,21 @@ __device__ __forceinline__ void write_node(float4* __restrict__ rec, const float
     rec[3] = make_float4(__int_as_float(link0), __int_as_float(link1), 0.f, 0.f);
 }
 
+// Format 2, "paired" 64 B record for the packed-FMA traversal (fma.rn.f32x2 -> FFMA2 on sm_100): the values that meet the
+// same pair of ray constants sit in adjacent, 8-byte aligned words
+//     n0 = (c0.x, c0.y, c1.x, c1.y)   n1 = (h0.x, h0.y, h1.x, h1.y)   n2 = (c0.z, c1.z, h0.z, h1.z)   n3 = (link0, link1, 0, 0)
+__device__ __forceinline__ void write_node_p(float4* __restrict__ rec, const float4 l0, const float4 h0, const float4 l1,
+                                             const float4 h1, int link0, int link1)
+{
+    float c0[3], e0[3], c1[3], e1[3];
+    to_centre_half(l0, h0, c0, e0);
+    to_centre_half(l1, h1, c1, e1);
+    rec[0] = make_float4(c0[0], c0[1], c1[0], c1[1]);
+    rec[1] = make_float4(e0[0], e0[1], e1[0], e1[1]);
+    rec[2] = make_float4(c0[2], c1[2], e0[2], e1[2]);
+    rec[3] = make_float4(__int_as_float(link0), __int_as_float(link1), 0.f, 0.f);
+}
+
 // 32-byte record: (x0 y0 z0 link0)(x1 y1 z1 link1), each axis word = qlo | qhi << 16 with x = o + q * s.
 // Conservative by construction: lo is rounded down and hi up to the cell grid and both are moved out by one more cell,
 // which covers the rounding of this division (< 0.01 cell) and of the traversal's decode (< 0.6 cell, traverse.cuh).
@@ -374,6 +389,15 @@ __device__ __forceinline__ void write_node_q(float4* __restrict__ rec, const Nod
                          __uint_as_float(quant_axis(l0.z, h0.z, q.o[2], q.s[2])), __int_as_float(link0));
     rec[1] = make_float4(__uint_as_float(quant_axis(l1.x, h1.x, q.o[0], q.s[0])), __uint_as_float(quant_axis(l1.y, h1.y, q.o[1], q.s[1])),
                          __uint_as_float(quant_axis(l1.z, h1.z, q.o[2], q.s[2])), __int_as_float(link1));
+}
+
+// one node record in the format of the tree being built (0: centre/half float4 x 4, 1: 16-bit boxes, 2: paired)
+__device__ __forceinline__ void emit_node(float4* __restrict__ nodes_out, int64_t idx, int format, const NodeQ& nq, const float4 l0,
+                                          const float4 h0, const float4 l1, const float4 h1, int link0, int link1)
+{
+    if (format == 0) write_node(nodes_out + 4 * idx, l0, h0, l1, h1, link0, link1);
+    else if (format == 2) write_node_p(nodes_out + 4 * idx, l0, h0, l1, h1, link0, link1);
+    else write_node_q(nodes_out + 2 * idx, nq, l0, h0, l1, h1, link0, link1);
 }
 
 __global__ void k_refit(int n, const int* __restrict__ parent_leaf, const int* __restrict__ parent_node,
@@ -400,8 +424,7 @@ __global__ void k_refit(int n, const int* __restrict__ parent_leaf, const int* _
         int k0 = ch.x, k1 = ch.y;
         if (k0 >= 0 && range[k0].y <= leaf_max) k0 = ~(range[k0].x | ((range[k0].y - 1) << 28));
         if (k1 >= 0 && range[k1].y <= leaf_max) k1 = ~(range[k1].x | ((range[k1].y - 1) << 28));
-        if (format == 0) write_node(nodes_out + 4 * (int64_t)cur, l0, h0, l1, h1, k0, k1);
-        else write_node_q(nodes_out + 2 * (int64_t)cur, nq, l0, h0, l1, h1, k0, k1);
+        emit_node(nodes_out, cur, format, nq, l0, h0, l1, h1, k0, k1);
         int up = parent_node[cur];
         if (up < 0) {
             meta->height = (int)height;
@@ -418,8 +441,7 @@ __global__ void k_single_leaf_root(const float4* leaf_lo, const float4* leaf_hi,
                                    NodeQ nq)
 {
     float4 l = leaf_lo[0], h = leaf_hi[0];
-    if (format == 0) write_node(nodes_out, l, h, l, h, ~0, ~0);
-    else write_node_q(nodes_out, nq, l, h, l, h, ~0, ~0);
+    emit_node(nodes_out, 0, format, nq, l, h, l, h, ~0, ~0);
     meta->height = 1;
     meta->root_lo[0] = l.x; meta->root_lo[1] = l.y; meta->root_lo[2] = l.z;
     meta->root_hi[0] = h.x; meta->root_hi[1] = h.y; meta->root_hi[2] = h.z;
@@ -464,6 +486,11 @@ __global__ void k_sah_sum(const float4* __restrict__ nodes, int64_t n_nodes, dou
             continue;
         }
         const float4 n0 = nodes[4 * i], n1 = nodes[4 * i + 1], n2 = nodes[4 * i + 2];
+        if (format == 2) {
+            acc += 8.0 * ((double)n1.x * n1.y + (double)n1.y * n2.z + (double)n2.z * n1.x);   // child 0: h = (n1.x, n1.y, n2.z)
+            acc += 8.0 * ((double)n1.z * n1.w + (double)n1.w * n2.w + (double)n2.w * n1.z);   // child 1: h = (n1.z, n1.w, n2.w)
+            continue;
+        }
         acc += 8.0 * ((double)n0.w * n1.x + (double)n1.x * n1.y + (double)n1.y * n0.w);   // child 0: h = (n0.w, n1.x, n1.y)
         acc += 8.0 * ((double)n2.y * n2.z + (double)n2.z * n2.w + (double)n2.w * n2.y);   // child 1: h = (n2.y, n2.z, n2.w)
     }
@@ -497,7 +524,7 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
     const int64_t n_nodes = T > 1 ? T - 1 : 1;
     const int format = (int)ctx->opt_node_format;
     {
-        const size_t nodes_bytes = align_up(sizeof(float4) * (format == 0 ? 4 : 2) * (size_t)n_nodes, 256);
+        const size_t nodes_bytes = align_up(sizeof(float4) * (format == 1 ? 2 : 4) * (size_t)n_nodes, 256);
         const size_t tris_bytes = align_up(sizeof(float4) * 3 * (size_t)T, 256);
         int rcb = lrc_grow(ctx, &ctx->bvh_block, &ctx->bvh_block_bytes, nodes_bytes + tris_bytes);
         if (rcb) return rcb;
@@ -683,7 +710,7 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
         ctx->root_area = 2.0 * ((double)ex * ey + (double)ey * ez + (double)ez * ex);
         inf.sah_cost = -1.f;   // computed on demand by lrc_bvh_get_info
     }
-    inf.bytes_nodes = (int64_t)sizeof(float4) * (format == 0 ? 4 : 2) * n_nodes;
+    inf.bytes_nodes = (int64_t)sizeof(float4) * (format == 1 ? 2 : 4) * n_nodes;
     inf.bytes_tris = (int64_t)sizeof(float4) * 3 * T;
     if (hm.height + 1 >= LRC_STACK_DEPTH && quality) {
         // a PLOC tree has no height bound; the radix tree's is the key length -- rebuild with it rather than fail

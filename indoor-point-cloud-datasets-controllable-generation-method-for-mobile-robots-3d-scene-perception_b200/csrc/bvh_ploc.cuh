@@ -15,9 +15,9 @@
 //                                   written to the other cluster buffer at their compacted position
 //   k_ploc_tail      once <= 1024 clusters are left: the same loop inside ONE block, clusters in shared memory
 //   k_ploc_positions every leaf / inner node walks to the root: first leaf slot of its subtree in depth-first order
-//   k_ploc_emit      64 B / 32 B node records at the IN-ORDER index (first slot + leaves on the left - 1): a subtree's
-//                    records and its triangles are contiguous, as in the radix tree; subtrees of <= leaf_size triangles
-//                    become one leaf link
+//   k_ploc_emit      64 B / 32 B node records, numbered like the radix tree's (left child = last leaf slot of the left
+//                    subtree, right child = that + 1, root 0): sibling records share a 128 B line and a subtree's records
+//                    and triangles are contiguous; subtrees of <= leaf_size triangles become one leaf link
 //   k_tri_records    48 B triangle records in depth-first leaf order
 // Merge decisions depend only on the data (ties: area, then a symmetric hash of the pair, then index), node ids come
 // from prefix sums, so every rank of a multi-GPU run builds the same tree.
@@ -304,9 +304,11 @@ __global__ void k_ploc_positions(int T, PlocTree tr, BuildMeta* meta)
     }
 }
 
+// link of a child that is (or collapses into) a leaf; `inner` is set when the child keeps its own node record instead
 __device__ __forceinline__ int ploc_link(const PlocTree& tr, int child, int leaf_max, const float4* leaf_lo, const float4* leaf_hi,
-                                         float4& lo, float4& hi)
+                                         float4& lo, float4& hi, bool& inner)
 {
+    inner = false;
     if (child < 0) {
         lo = leaf_lo[~child]; hi = leaf_hi[~child];
         return ~tr.start_leaf[~child];
@@ -314,7 +316,8 @@ __device__ __forceinline__ int ploc_link(const PlocTree& tr, int child, int leaf
     lo = tr.lo[child]; hi = tr.hi[child];
     const int cnt = __float_as_int(lo.w);
     if (cnt <= leaf_max) return ~(tr.start_node[child] | ((cnt - 1) << 28));
-    return tr.start_node[child] + tr.cl[child] - 1;          // in-order index of the child's record
+    inner = true;                                            // the caller knows the record index (a leaf link may be -1 itself)
+    return 0;
 }
 
 __global__ void k_ploc_emit(int T, PlocTree tr, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
@@ -322,17 +325,25 @@ __global__ void k_ploc_emit(int T, PlocTree tr, const float4* __restrict__ leaf_
 {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= T - 1) return;
+    // Record numbering of the radix tree (Karras 2012), which keeps SIBLING records adjacent (one 128 B line): with
+    // gamma = last depth-first leaf slot of the left subtree, the left child's record is gamma and the right child's gamma + 1;
+    // the root is 0.  (A left inner child ends at gamma, a right inner child starts at gamma + 1, and no two inner nodes
+    // share such an end / start slot, so the numbering is a bijection onto 0 .. T-2.)
     float4 l0, h0, l1, h1;
-    const int k0 = ploc_link(tr, tr.left[a], leaf_max, leaf_lo, leaf_hi, l0, h0);
-    const int k1 = ploc_link(tr, tr.right[a], leaf_max, leaf_lo, leaf_hi, l1, h1);
-    const int idx = tr.start_node[a] + tr.cl[a] - 1;
-    if (format == 0) write_node(nodes_out + 4 * (int64_t)idx, l0, h0, l1, h1, k0, k1);
-    else write_node_q(nodes_out + 2 * (int64_t)idx, nq, l0, h0, l1, h1, k0, k1);
-    if (a == T - 2) {                                        // the root is the last node created
+    const int gamma = tr.start_node[a] + tr.cl[a] - 1;
+    bool in0, in1;
+    int k0 = ploc_link(tr, tr.left[a], leaf_max, leaf_lo, leaf_hi, l0, h0, in0);
+    int k1 = ploc_link(tr, tr.right[a], leaf_max, leaf_lo, leaf_hi, l1, h1, in1);
+    if (in0) k0 = gamma;
+    if (in1) k1 = gamma + 1;
+    const int p = tr.parent_node[a];
+    const int idx = p < 0 ? 0 : tr.start_node[p] + tr.cl[p] - 1 + (tr.right[p] == a ? 1 : 0);
+    emit_node(nodes_out, idx, format, nq, l0, h0, l1, h1, k0, k1);
+    if (p < 0) {
         const float4 lo = tr.lo[a], hi = tr.hi[a];
         meta->root_lo[0] = lo.x; meta->root_lo[1] = lo.y; meta->root_lo[2] = lo.z;
         meta->root_hi[0] = hi.x; meta->root_hi[1] = hi.y; meta->root_hi[2] = hi.z;
-        meta->root = idx;
+        meta->root = 0;
     }
 }
 

@@ -123,6 +123,9 @@ struct lrc_ctx {
     size_t kt_used = 0;
 
     // ---- options ----
+    int64_t opt_rays_per_thread = 1;    // scan kernels: adjacent rays per thread (1, 2, 4); > 1 needs node format 2
+    int64_t opt_persistent = 0;         // 1: persistent warps over 32-ray tiles (VARIANT bit 8) instead of one block per 128 rays
+    int num_sms = 148;
     int64_t opt_block = 128;            // threads per traversal block
     int64_t opt_chunk_rays = 1 << 26;   // rays per traversal/epilogue chunk (bounds scratch: 16 B per ray)
     int64_t opt_variant = 1;            // traversal kernel variant: while-while loop (bit 2, the 32-register build, lost

@@ -166,25 +166,70 @@ struct FrameMath {
     double cx, cy, cz;         // frame centre for MODE_RAYS; scan modes read pose[:3,3]
 };
 
+// One ray's share of the frame arithmetic (see above): writes the scratch record of ray idx, returns whether it is kept.
+template <int MODE>
+__device__ __forceinline__ bool frame_epilogue(const RayGen& g, const FrameMath& fm, int64_t idx, int64_t pose, int r, float ox, float oy,
+                                               float oz, float dx, float dy, float dz, float t, uint32_t id, float4* __restrict__ hp,
+                                               double* __restrict__ inc_out)
+{
+    bool keep = false;
+    float4 o = make_float4(0.f, 0.f, 0.f, __uint_as_float(LRC_MISS_ID));
+    double inc = 0.0;
+    if (id != LRC_MISS_ID) {
+        if (g.range_std > 0.0) t = __fadd_rn(t, (float)(g.range_std * range_normal(g, pose, r)));
+        float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+        o.x = __fadd_rn(ox, __fmul_rn(__fdiv_rn(dx, nrm), t));
+        o.y = __fadd_rn(oy, __fmul_rn(__fdiv_rn(dy, nrm), t));
+        o.z = __fadd_rn(oz, __fmul_rn(__fdiv_rn(dz, nrm), t));
+        keep = true;
+        if (fm.max_range >= 0.0) {
+            double cx = fm.cx, cy = fm.cy, cz = fm.cz;
+            if (MODE != MODE_RAYS) {
+                const double* M = g.poses + 16 * (g.pose0 + pose);
+                cx = M[3]; cy = M[7]; cz = M[11];
+            }
+            const double ddx = __dsub_rn((double)o.x, cx), ddy = __dsub_rn((double)o.y, cy), ddz = __dsub_rn((double)o.z, cz);
+            const double dist = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz)));
+            keep = dist < fm.max_range;
+            if (inc_out) inc = __dmul_rn(acos(fabs(__ddiv_rn(ddz, dist))), 180.0 / PI_D);
+        }
+        if (keep) o.w = __uint_as_float(id);
+    }
+    hp[idx] = o;
+    if (inc_out) inc_out[idx] = inc;
+    return keep;
+}
+
 constexpr int TRACE_THREADS = 128;
 
 // OUT_DENSE: write (t_hit, prim_id) per ray (cast_rays).  Otherwise, per ray, the float32 hit point + triangle id
 // (float4; id = MISS when the ray missed, was dropped or failed the range test), the incident angle, and per BLOCK
 // the number of kept rays (block_count) -- the first stage of the ordered compaction.
+// VARIANT bit 8 ("persistent"): the grid is sized to fill the machine once and every WARP walks over 32-ray tiles with a
+// static stride (tile = warp number + k * warps in the grid) -- no block-wide barrier parks finished warps behind the block's
+// slowest ray (ncu, round 1: 2.75 warps per issue slot stalled at the barrier), every resident warp always has a ray.  The
+// per-block keep counts the compaction needs are then accumulated with one atomicAdd per tile (integer adds commute, so the
+// counts -- and the output order -- stay deterministic); the launcher zeroes them first.
 template <int MODE, bool COUNT, bool OUT_DENSE, int VARIANT>
 __global__ void __launch_bounds__(TRACE_THREADS, (VARIANT & 4) ? 16 : 12)   // 40 registers (48 warps per SM); VARIANT bit 2: 32 registers (64 warps)
 k_trace(RayGen g, FrameMath fm, const float4* __restrict__ nodes, const float4* __restrict__ tris, int64_t n, int has_tris,
         float4* __restrict__ hp, double* __restrict__ inc_out, unsigned* __restrict__ block_count, float* __restrict__ t_hit,
         uint32_t* __restrict__ prim_id, unsigned long long* counters, const float4* __restrict__ top_table, int top_n,
-        int stack_levels, const __grid_constant__ NodeQ nq, int root)
+        int stack_levels, const __grid_constant__ NodeQ nq, int root, int tile_shift)
 {
     extern __shared__ float4 s_top[];
+    constexpr bool PERSIST = (VARIANT & 256) != 0;
     if (VARIANT & 8) {      // stage the top of the tree (heap order, built by lrc_set_mesh) in shared memory
         for (int i = threadIdx.x; i < 4 * top_n; i += blockDim.x) s_top[i] = __ldg(top_table + i);
         __syncthreads();
     }
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned nn = 0, nt = 0, nr = 0, nh = 0;
+    const int64_t n_tiles = (n + 31) >> 5;
+    const int64_t tile_stride = (int64_t)gridDim.x * (blockDim.x >> 5);
+    int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (PERSIST && tile >= n_tiles) return;
+    do {
+    const int64_t idx = PERSIST ? (tile << 5) + lane_id() : (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool keep = false;
     if (idx < n) {
         int64_t pose; int r;
@@ -193,43 +238,87 @@ k_trace(RayGen g, FrameMath fm, const float4* __restrict__ nodes, const float4* 
         uint32_t id = LRC_MISS_ID;
         if (ray.keep && has_tris) {
             trace_ray<VARIANT, COUNT>(nodes, tris, s_top, top_n, stack_levels, nq, root, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, t, id, nn, nt);
-            nr = 1;
-            nh = id != LRC_MISS_ID;
+            nr += 1;
+            nh += id != LRC_MISS_ID;
         }
         if (OUT_DENSE) {
             t_hit[idx] = t;
             prim_id[idx] = id;
         } else {
-            float4 o = make_float4(0.f, 0.f, 0.f, __uint_as_float(LRC_MISS_ID));
-            double inc = 0.0;
-            if (id != LRC_MISS_ID) {
-                if (g.range_std > 0.0) t = __fadd_rn(t, (float)(g.range_std * range_normal(g, pose, r)));
-                float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ray.dx, ray.dx), __fmul_rn(ray.dy, ray.dy)), __fmul_rn(ray.dz, ray.dz)));
-                o.x = __fadd_rn(ray.ox, __fmul_rn(__fdiv_rn(ray.dx, nrm), t));
-                o.y = __fadd_rn(ray.oy, __fmul_rn(__fdiv_rn(ray.dy, nrm), t));
-                o.z = __fadd_rn(ray.oz, __fmul_rn(__fdiv_rn(ray.dz, nrm), t));
-                keep = true;
-                if (fm.max_range >= 0.0) {
-                    double cx = fm.cx, cy = fm.cy, cz = fm.cz;
-                    if (MODE != MODE_RAYS) {
-                        const double* M = g.poses + 16 * (g.pose0 + pose);
-                        cx = M[3]; cy = M[7]; cz = M[11];
-                    }
-                    const double ddx = __dsub_rn((double)o.x, cx), ddy = __dsub_rn((double)o.y, cy), ddz = __dsub_rn((double)o.z, cz);
-                    const double dist = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz)));
-                    keep = dist < fm.max_range;
-                    if (inc_out) inc = __dmul_rn(acos(fabs(__ddiv_rn(ddz, dist))), 180.0 / PI_D);
-                }
-                if (keep) o.w = __uint_as_float(id);
-            }
-            hp[idx] = o;
-            if (inc_out) inc_out[idx] = inc;
+            keep = frame_epilogue<MODE>(g, fm, idx, pose, r, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, t, id, hp, inc_out);
         }
     }
     if (!OUT_DENSE) {
-        const int c = __syncthreads_count(keep ? 1 : 0);
-        if (threadIdx.x == 0) block_count[blockIdx.x] = (unsigned)c;
+        if (PERSIST) {
+            const unsigned b = __ballot_sync(0xffffffffu, keep);
+            if (lane_id() == 0 && b) atomicAdd(&block_count[tile >> tile_shift], (unsigned)__popc(b));
+        } else {
+            const int c = __syncthreads_count(keep ? 1 : 0);
+            if (threadIdx.x == 0) block_count[blockIdx.x] = (unsigned)c;
+        }
     }
+    tile += tile_stride;
+    } while (PERSIST && tile < n_tiles);
+    if (COUNT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            nn += __shfl_xor_sync(0xffffffffu, nn, o);
+            nt += __shfl_xor_sync(0xffffffffu, nt, o);
+            nr += __shfl_xor_sync(0xffffffffu, nr, o);
+            nh += __shfl_xor_sync(0xffffffffu, nh, o);
+        }
+        if (lane_id() == 0) {
+            atomicAdd(&counters[0], (unsigned long long)nr);
+            atomicAdd(&counters[1], (unsigned long long)nn);
+            atomicAdd(&counters[2], (unsigned long long)nt);
+            atomicAdd(&counters[3], (unsigned long long)nh);
+        }
+    }
+}
+
+// K adjacent rays per thread (traverse.cuh "thread packets"): block = 128 threads = 128 K rays = K blocks of the compaction.
+template <int MODE, bool COUNT, int K>
+__global__ void __launch_bounds__(TRACE_THREADS, K == 2 ? 8 : 5)
+k_trace_k(RayGen g, FrameMath fm, const float4* __restrict__ nodes, const float4* __restrict__ tris, int64_t n, int has_tris,
+          float4* __restrict__ hp, double* __restrict__ inc_out, unsigned* __restrict__ block_count, unsigned long long* counters, int root)
+{
+    __shared__ unsigned s_cnt[K];
+    if (threadIdx.x < K) s_cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    const int64_t base = ((int64_t)blockIdx.x * TRACE_THREADS + threadIdx.x) * K;
+    Packet<K> pk;
+    unsigned nn = 0, nt = 0, nr = 0, nh = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int64_t idx = base + k;
+        if (idx < n) {
+            int64_t pose; int r;
+            const Ray ray = gen_ray<MODE>(g, idx, pose, r);
+            const bool live = ray.keep && has_tris;
+            packet_set_ray<K>(pk, k, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, live);
+            nr += live;
+        } else {
+            packet_set_ray<K>(pk, k, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, false);
+        }
+    }
+    if (base < n && has_tris) trace_packet<K, COUNT>(nodes, tris, root, pk, nn, nt);
+    unsigned kept = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int64_t idx = base + k;
+        if (idx < n) {
+            int64_t pose = 0; int r = (int)idx;
+            if (MODE != MODE_RAYS) { pose = idx / g.N; r = (int)(idx - pose * g.N); }
+            const uint32_t id = pk.best_id[k];
+            nh += id != LRC_MISS_ID;
+            kept += frame_epilogue<MODE>(g, fm, idx, pose, r, pk.ox[k], pk.oy[k], pk.oz[k], pk.dx[k], pk.dy[k], pk.dz[k], pk.best_t[k], id, hp, inc_out);
+        }
+    }
+    // keep counts per 128 rays: sub-block j of this block = threads [j * 128 / K, (j + 1) * 128 / K), i.e. whole warps
+    const unsigned wsum = __reduce_add_sync(0xffffffffu, kept);
+    if (lane_id() == 0 && wsum) atomicAdd(&s_cnt[(threadIdx.x * K) / TRACE_THREADS], wsum);
+    __syncthreads();
+    if (threadIdx.x < K && ((int64_t)blockIdx.x * K + threadIdx.x) * TRACE_THREADS < n) block_count[(int64_t)blockIdx.x * K + threadIdx.x] = s_cnt[threadIdx.x];
     if (COUNT) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -479,17 +568,32 @@ int ensure_counters(lrc_ctx* ctx)
     return LRC_OK;
 }
 
+// rays per thread of the scan kernels: > 1 needs the paired node records (format 2) and 128-ray compaction blocks
+inline int packet_rays(const lrc_ctx* ctx) { return ctx->node_format == 2 ? (int)ctx->opt_rays_per_thread : 1; }
+inline int scan_block_threads(const lrc_ctx* ctx) { return packet_rays(ctx) > 1 ? TRACE_THREADS : (int)ctx->opt_block; }
+
 template <int MODE, bool DENSE>
 int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, float4* hp, double* inc, unsigned* block_count,
                  float* t_hit, uint32_t* prim, cudaStream_t stream)
 {
     if (n <= 0) return LRC_OK;
-    const int TB = DENSE ? TRACE_THREADS : (int)ctx->opt_block;
-    const unsigned grid = (unsigned)((n + TB - 1) / TB);
     const int has_tris = ctx->T > 0;
+    if (!DENSE && packet_rays(ctx) > 1) {
+        // K adjacent rays per thread (paired node records only)
+        const int K = packet_rays(ctx);
+        const unsigned pgrid = (unsigned)((n + (int64_t)TRACE_THREADS * K - 1) / ((int64_t)TRACE_THREADS * K));
+#define LRC_LAUNCH_PACKET(COUNT, KK) \
+        k_trace_k<MODE, COUNT, KK><<<pgrid, TRACE_THREADS, 0, stream>>>(g, fm, ctx->nodes, ctx->tris, n, has_tris, hp, inc, block_count, ctx->d_counters, ctx->root)
+        if (ctx->counting) { if (K == 2) LRC_LAUNCH_PACKET(true, 2); else LRC_LAUNCH_PACKET(true, 4); }
+        else { if (K == 2) LRC_LAUNCH_PACKET(false, 2); else LRC_LAUNCH_PACKET(false, 4); }
+#undef LRC_LAUNCH_PACKET
+        LRC_CHECK_LAUNCH(ctx, "k_trace_k");
+        return LRC_OK;
+    }
+    const int TB = DENSE ? TRACE_THREADS : (int)ctx->opt_block;
+    unsigned grid = (unsigned)((n + TB - 1) / TB);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3((unsigned)TB); cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     cfg.attrs = attr;
     if (ctx->opt_l2_persist && ctx->l2_persist_max > 0 && ctx->bvh_bytes > 0) {
@@ -511,13 +615,25 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
     const NodeQ nq = ctx->nodeq;
     const int root = ctx->root;
     // the resident tree's record format selects the kernel family; the variant option tunes the float-format kernels
-    const int64_t variant = ctx->node_format == 1 ? 37 : ctx->opt_variant;
+    int64_t variant = ctx->node_format == 1 ? 37 : ctx->node_format == 2 ? ((ctx->opt_variant & 64) ? 193 : 129) : ctx->opt_variant;
+    int tile_shift = 0;
+    if (ctx->opt_persistent && (variant == 1 || variant == 65 || variant == 129 || variant == 193)) {
+        variant |= 256;
+        const unsigned fill = (unsigned)(ctx->num_sms * 12 * (TRACE_THREADS / TB));      // blocks that are resident at once
+        if (grid > fill) grid = fill;
+        tile_shift = TB == 128 ? 2 : TB == 64 ? 1 : 0;
+        if (block_count) {     // per-block keep counts are accumulated with atomics: start from zero
+            cudaError_t me = cudaMemsetAsync(block_count, 0, sizeof(unsigned) * (size_t)((n + TB - 1) / TB), stream);
+            if (me != cudaSuccess) return lrc_fail(ctx, LRC_ERR_CUDA, "cudaMemsetAsync(block counts): %s", cudaGetErrorString(me));
+        }
+    }
     const int top_n = (variant & 8) ? (int)((1 << ctx->opt_top_levels) - 1) : 0;
     const int stack_levels = (variant & 16) ? (int)ctx->opt_stack_levels : 0;
     cfg.dynamicSmemBytes = (variant & 16) ? (size_t)stack_levels * LRC_SS_STRIDE * sizeof(int) : (size_t)top_n * 64;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3((unsigned)TB); cfg.stream = stream;
     cudaError_t le = cudaSuccess;
 #define LRC_LAUNCH_TRACE(COUNT, VARIANT) \
-    le = cudaLaunchKernelEx(&cfg, k_trace<MODE, COUNT, DENSE, VARIANT>, g, fm, nodes, tris, n, has_tris, hp, inc, block_count, t_hit, prim, counters, top_table, top_n, stack_levels, nq, root)
+    le = cudaLaunchKernelEx(&cfg, k_trace<MODE, COUNT, DENSE, VARIANT>, g, fm, nodes, tris, n, has_tris, hp, inc, block_count, t_hit, prim, counters, top_table, top_n, stack_levels, nq, root, tile_shift)
     if (ctx->counting) {
         switch (variant) {
             case 0: LRC_LAUNCH_TRACE(true, 0); break;
@@ -528,6 +644,12 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
             case 21: LRC_LAUNCH_TRACE(true, 21); break;
             case 37: LRC_LAUNCH_TRACE(true, 37); break;
             case 65: LRC_LAUNCH_TRACE(true, 65); break;
+            case 129: LRC_LAUNCH_TRACE(true, 129); break;
+            case 193: LRC_LAUNCH_TRACE(true, 193); break;
+            case 257: LRC_LAUNCH_TRACE(true, 257); break;
+            case 321: LRC_LAUNCH_TRACE(true, 321); break;
+            case 385: LRC_LAUNCH_TRACE(true, 385); break;
+            case 449: LRC_LAUNCH_TRACE(true, 449); break;
             default: LRC_LAUNCH_TRACE(true, 3); break;
         }
     } else {
@@ -540,6 +662,12 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
             case 21: LRC_LAUNCH_TRACE(false, 21); break;
             case 37: LRC_LAUNCH_TRACE(false, 37); break;
             case 65: LRC_LAUNCH_TRACE(false, 65); break;
+            case 129: LRC_LAUNCH_TRACE(false, 129); break;
+            case 193: LRC_LAUNCH_TRACE(false, 193); break;
+            case 257: LRC_LAUNCH_TRACE(false, 257); break;
+            case 321: LRC_LAUNCH_TRACE(false, 321); break;
+            case 385: LRC_LAUNCH_TRACE(false, 385); break;
+            case 449: LRC_LAUNCH_TRACE(false, 449); break;
             default: LRC_LAUNCH_TRACE(false, 3); break;
         }
     }
@@ -593,7 +721,7 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
     const bool piped = n_chunks > 1;
     const int n_slots = piped ? 2 : 1;
     const int64_t chunk_rays = frames_per_chunk * N;
-    const int TB = (int)ctx->opt_block;
+    const int TB = scan_block_threads(ctx);
     const int64_t max_blocks = (chunk_rays + TB - 1) / TB;
     const bool want_inc = out->incident_deg != nullptr && max_range >= 0.0;
     const size_t hp_bytes = align_up(sizeof(float4) * (size_t)chunk_rays, 256);
@@ -784,6 +912,7 @@ extern "C" int lrc_create(int device, lrc_ctx** out)
     ctx->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
     ctx->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     ctx->l2_size = (size_t)prop.l2CacheSize;
+    ctx->num_sms = prop.multiProcessorCount;
     *out = ctx;
     return LRC_OK;
 }
@@ -890,7 +1019,7 @@ extern "C" int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value)
         return LRC_OK;
     }
     if (!strcmp(key, "node_format")) {
-        if (value != 0 && value != 1) return lrc_fail(ctx, LRC_ERR_INVALID, "node_format must be 0 (64 B float boxes) or 1 (32 B 16-bit boxes)");
+        if (value < 0 || value > 2) return lrc_fail(ctx, LRC_ERR_INVALID, "node_format must be 0 (64 B float boxes), 1 (32 B 16-bit boxes) or 2 (64 B paired boxes, packed FMA)");
         ctx->opt_node_format = value;      // takes effect at the next lrc_set_mesh
         return LRC_OK;
     }
@@ -912,6 +1041,12 @@ extern "C" int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value)
         ctx->opt_block = value;
         return LRC_OK;
     }
+    if (!strcmp(key, "rays_per_thread")) {
+        if (value != 1 && value != 2 && value != 4) return lrc_fail(ctx, LRC_ERR_INVALID, "rays_per_thread must be 1, 2 or 4");
+        ctx->opt_rays_per_thread = value;
+        return LRC_OK;
+    }
+    if (!strcmp(key, "persistent")) { ctx->opt_persistent = value != 0; return LRC_OK; }
     if (!strcmp(key, "kernel_timing")) { ctx->opt_kernel_timing = value != 0; ctx->kt_used = 0; return LRC_OK; }
     if (!strcmp(key, "variant")) {
         if (value < 0 || (value > 3 && value != 5 && value != 13 && value != 21 && value != 65)) return lrc_fail(ctx, LRC_ERR_INVALID, "variant must be 0..3, 5, 13, 21 or 65");

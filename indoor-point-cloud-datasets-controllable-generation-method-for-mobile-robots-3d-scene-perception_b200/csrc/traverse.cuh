@@ -289,12 +289,222 @@ __device__ __forceinline__ int inner_step_q(const float4* __restrict__ nodes, in
     return StackOps<STACK>::pop(stack, sp, best_t, sm, levels);
 }
 
+// ---- paired 64 B nodes + packed FP32 FMA (node format 2) -------------------------------------------------------------
+// k_trace is bound by issue slots (ncu: 71 % of issue cycles busy, FMA pipe 30 %): 18 of the ~45 instructions of one inner
+// step are the scalar FFMAs of the two slab tests.  sm_100 has a two-wide FP32 FMA (PTX fma.rn.f32x2 -> SASS FFMA2): one
+// issue slot, two fused multiply-adds on an aligned register pair.  The paired record (bvh_build.cu write_node_p) puts the
+// values that meet the same pair of ray constants next to each other, so one inner step is 9 FFMA2 instead of 18 FFMA --
+// each lane-wise result is the same fused operation as before, so culling decisions (and node counts) are unchanged.
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c)
+{
+    unsigned long long ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rd));
+    return r;
+}
+
+struct RaySlabP {
+    float2 ixy, izz;       // 1/d
+    float2 axy, azz;       // |1/d|
+    float2 nxy, nzz;       // -o/d
+};
+
+__device__ __forceinline__ RaySlabP make_slab_p(float ox, float oy, float oz, float dx, float dy, float dz)
+{
+    const RaySlab r = make_slab(ox, oy, oz, dx, dy, dz);
+    RaySlabP s;
+    s.ixy = make_float2(r.ix, r.iy); s.izz = make_float2(r.iz, r.iz);
+    s.axy = make_float2(r.ax, r.ay); s.azz = make_float2(r.az, r.az);
+    s.nxy = make_float2(r.nx, r.ny); s.nzz = make_float2(r.nz, r.nz);
+    return s;
+}
+
+template <bool COUNT, class STACK>
+__device__ __forceinline__ int inner_step_p(const float4* __restrict__ nodes, int cur, const RaySlabP& s, float best_t,
+                                            STACK& stack, int& sp, unsigned& n_nodes)
+{
+    const float4* np = nodes + 4 * (int64_t)cur;
+    const float4 A = __ldg(np + 0), B = __ldg(np + 1), Z = __ldg(np + 2);
+    const float2 L = __ldg(reinterpret_cast<const float2*>(np + 3));
+    if (COUNT) ++n_nodes;
+    const float2 naxy = make_float2(-s.axy.x, -s.axy.y), nazz = make_float2(-s.azz.x, -s.azz.y);
+    const float2 tc0 = ffma2(make_float2(A.x, A.y), s.ixy, s.nxy);      // child 0: (x, y) slab centres
+    const float2 tc1 = ffma2(make_float2(A.z, A.w), s.ixy, s.nxy);      // child 1
+    const float2 tcz = ffma2(make_float2(Z.x, Z.y), s.izz, s.nzz);      // z slab centres of child 0 | child 1
+    const float2 n0 = ffma2(make_float2(B.x, B.y), naxy, tc0), f0 = ffma2(make_float2(B.x, B.y), s.axy, tc0);
+    const float2 n1 = ffma2(make_float2(B.z, B.w), naxy, tc1), f1 = ffma2(make_float2(B.z, B.w), s.axy, tc1);
+    const float2 nz = ffma2(make_float2(Z.z, Z.w), nazz, tcz), fz = ffma2(make_float2(Z.z, Z.w), s.azz, tcz);
+    const float t0 = fmaxf(fmaxf(n0.x, n0.y), fmaxf(nz.x, 0.f)), e0 = fminf(fminf(f0.x, f0.y), fminf(fz.x, best_t));
+    const float t1 = fmaxf(fmaxf(n1.x, n1.y), fmaxf(nz.y, 0.f)), e1 = fminf(fminf(f1.x, f1.y), fminf(fz.y, best_t));
+    const bool h0 = t0 <= e0, h1 = t1 <= e1;
+    const int l0 = __float_as_int(L.x), l1 = __float_as_int(L.y);
+    if (h0 && h1) {
+        const bool swp = t1 < t0;
+        StackOps<STACK>::push(stack, sp, swp ? l0 : l1, swp ? t0 : t1, nullptr, 0);
+        return swp ? l1 : l0;
+    }
+    if (h0) return l0;
+    if (h1) return l1;
+    return StackOps<STACK>::pop(stack, sp, best_t, nullptr, 0);
+}
+
+template <bool COUNT, class STACK>
+__device__ __forceinline__ void trace_loop_p(const float4* __restrict__ nodes, const float4* __restrict__ tris, int root, float ox,
+                                             float oy, float oz, float dx, float dy, float dz, float& best_t, uint32_t& best_id,
+                                             unsigned& n_nodes, unsigned& n_tris)
+{
+    best_t = LRC_INF;
+    best_id = LRC_MISS_ID;
+    const RaySlabP s = make_slab_p(ox, oy, oz, dx, dy, dz);
+    STACK stack;
+    int sp = 0;
+    int cur = root;
+    while (cur != LRC_SENTINEL) {
+        while (cur >= 0) cur = inner_step_p<COUNT>(nodes, cur, s, best_t, stack, sp, n_nodes);
+        if (cur != LRC_SENTINEL) {
+            leaf_test(tris, cur, ox, oy, oz, dx, dy, dz, best_t, best_id, n_tris);
+            cur = StackOps<STACK>::pop(stack, sp, best_t, nullptr, 0);
+        }
+    }
+}
+
+// ---- K rays per thread ("thread packets", paired node format) -----------------------------------------------------------
+// What bounds the one-ray-per-thread kernel is neither HBM nor issue slots but the L1 -> register return path (ncu round 1:
+// l1tex data-pipe wavefronts 75-80 % of peak, LSU write-back active 62 %): every lane pulls the 56 bytes of a node record
+// into its own registers -- 14 cycles of the SM's 128 B/clk return path per warp and node, however uniform the addresses
+// are (which is why neither shared-memory staging nor packed FMA moved the time).  The K rays of one thread are adjacent
+// azimuths of one scan line (0.09 deg apart for the 32-line sensor): they walk almost the same nodes, so the thread fetches
+// each record ONCE and tests it against all K rays -- 56/K bytes of write-back per ray and node, 1/K of the stack traffic
+// and loop control.  A node is entered when ANY ray of the packet hits its box; each ray still culls with its own best
+// hit, and the Moller-Trumbore test per ray is the unchanged bit-exact one, so results are identical -- the packet only
+// visits the UNION of its rays' nodes.  Ray pairs share one FFMA2 per slab plane (node scalar broadcast to both halves).
+template <int K> struct Packet {
+    float ox[K], oy[K], oz[K], dx[K], dy[K], dz[K];
+    float ix[K], iy[K], iz[K], nx[K], ny[K], nz[K];
+    float best_t[K];
+    uint32_t best_id[K];
+};
+
+template <int K>
+__device__ __forceinline__ void packet_set_ray(Packet<K>& pk, int r, float ox, float oy, float oz, float dx, float dy, float dz, bool live)
+{
+    pk.ox[r] = ox; pk.oy[r] = oy; pk.oz[r] = oz; pk.dx[r] = dx; pk.dy[r] = dy; pk.dz[r] = dz;
+    const RaySlab s = make_slab(ox, oy, oz, dx, dy, dz);
+    pk.ix[r] = s.ix; pk.iy[r] = s.iy; pk.iz[r] = s.iz; pk.nx[r] = s.nx; pk.ny[r] = s.ny; pk.nz[r] = s.nz;
+    pk.best_t[r] = live ? LRC_INF : -1.f;      // a ray that is not cast (past the end, dropped) can never enter a box: tfar < 0 <= tnear
+    pk.best_id[r] = LRC_MISS_ID;
+}
+
+// slab planes of one axis of one child box for the ray pair (a, b): entry / exit distances
+__device__ __forceinline__ void slab_axis2(float c, float h, const float2 I, const float2 N, float2& tn, float2& tf)
+{
+    const float2 cc = make_float2(c, c), hh = make_float2(h, h);
+    const float2 A = make_float2(fabsf(I.x), fabsf(I.y));
+    const float2 tc = ffma2(cc, I, N);
+    tn = ffma2(hh, make_float2(-A.x, -A.y), tc);
+    tf = ffma2(hh, A, tc);
+}
+
+template <int K, bool COUNT, class STACK>
+__device__ __forceinline__ int inner_step_k(const float4* __restrict__ nodes, int cur, const Packet<K>& pk, STACK& stack, int& sp,
+                                            float bmax, unsigned& n_nodes)
+{
+    const float4* np = nodes + 4 * (int64_t)cur;
+    const float4 A = __ldg(np + 0), B = __ldg(np + 1), Z = __ldg(np + 2);
+    const float2 L = __ldg(reinterpret_cast<const float2*>(np + 3));
+    if (COUNT) ++n_nodes;
+    float m0 = LRC_INF, m1 = LRC_INF;             // smallest entry distance among the rays that hit child 0 / child 1
+#pragma unroll
+    for (int p = 0; p < K; p += 2) {
+        const float2 Ix = make_float2(pk.ix[p], pk.ix[p + 1]), Iy = make_float2(pk.iy[p], pk.iy[p + 1]), Iz = make_float2(pk.iz[p], pk.iz[p + 1]);
+        const float2 Nx = make_float2(pk.nx[p], pk.nx[p + 1]), Ny = make_float2(pk.ny[p], pk.ny[p + 1]), Nz = make_float2(pk.nz[p], pk.nz[p + 1]);
+        float2 nx0, fx0, ny0, fy0, nz0, fz0, nx1, fx1, ny1, fy1, nz1, fz1;
+        slab_axis2(A.x, B.x, Ix, Nx, nx0, fx0); slab_axis2(A.y, B.y, Iy, Ny, ny0, fy0); slab_axis2(Z.x, Z.z, Iz, Nz, nz0, fz0);
+        slab_axis2(A.z, B.z, Ix, Nx, nx1, fx1); slab_axis2(A.w, B.w, Iy, Ny, ny1, fy1); slab_axis2(Z.y, Z.w, Iz, Nz, nz1, fz1);
+        {
+            const float t0 = fmaxf(fmaxf(nx0.x, ny0.x), fmaxf(nz0.x, 0.f)), e0 = fminf(fminf(fx0.x, fy0.x), fminf(fz0.x, pk.best_t[p]));
+            const float t1 = fmaxf(fmaxf(nx1.x, ny1.x), fmaxf(nz1.x, 0.f)), e1 = fminf(fminf(fx1.x, fy1.x), fminf(fz1.x, pk.best_t[p]));
+            m0 = fminf(m0, t0 <= e0 ? t0 : LRC_INF);
+            m1 = fminf(m1, t1 <= e1 ? t1 : LRC_INF);
+        }
+        {
+            const float t0 = fmaxf(fmaxf(nx0.y, ny0.y), fmaxf(nz0.y, 0.f)), e0 = fminf(fminf(fx0.y, fy0.y), fminf(fz0.y, pk.best_t[p + 1]));
+            const float t1 = fmaxf(fmaxf(nx1.y, ny1.y), fmaxf(nz1.y, 0.f)), e1 = fminf(fminf(fx1.y, fy1.y), fminf(fz1.y, pk.best_t[p + 1]));
+            m0 = fminf(m0, t0 <= e0 ? t0 : LRC_INF);
+            m1 = fminf(m1, t1 <= e1 ? t1 : LRC_INF);
+        }
+    }
+    const bool h0 = m0 < LRC_INF, h1 = m1 < LRC_INF;
+    const int l0 = __float_as_int(L.x), l1 = __float_as_int(L.y);
+    if (h0 && h1) {
+        const bool swp = m1 < m0;                   // the child some ray enters first goes first, the other one on the stack
+        StackOps<STACK>::push(stack, sp, swp ? l0 : l1, swp ? m0 : m1, nullptr, 0);
+        return swp ? l1 : l0;
+    }
+    if (h0) return l0;
+    if (h1) return l1;
+    return StackOps<STACK>::pop(stack, sp, bmax, nullptr, 0);
+}
+
+template <int K>
+__device__ __forceinline__ void leaf_test_k(const float4* __restrict__ tris, int link, Packet<K>& pk, unsigned& n_tris)
+{
+    const unsigned x = ~(unsigned)link;
+    unsigned slot = x & 0x0fffffffu;
+    const unsigned last = slot + (x >> 28);
+#pragma unroll 1
+    do {
+        const float4* tp = tris + 3 * (int64_t)slot;
+        const float4 v0 = __ldg(tp + 0), e1 = __ldg(tp + 1), e2 = __ldg(tp + 2);
+        const uint32_t id = __float_as_uint(v0.w);
+        ++n_tris;
+#pragma unroll
+        for (int r = 0; r < K; ++r) {
+            float t;
+            if (mt_hit(pk.ox[r], pk.oy[r], pk.oz[r], pk.dx[r], pk.dy[r], pk.dz[r], v0, e1, e2, t)) {
+                if (t < pk.best_t[r] || (t == pk.best_t[r] && id < pk.best_id[r])) { pk.best_t[r] = t; pk.best_id[r] = id; }
+            }
+        }
+    } while (slot++ != last);
+}
+
+template <int K> __device__ __forceinline__ float packet_bmax(const Packet<K>& pk)
+{
+    float b = pk.best_t[0];
+#pragma unroll
+    for (int r = 1; r < K; ++r) b = fmaxf(b, pk.best_t[r]);
+    return b;
+}
+
+// closest hits of the K rays in pk (best_t = +inf / id = MISS on a miss; rays set up with live = false stay at -1 / MISS)
+template <int K, bool COUNT>
+__device__ __forceinline__ void trace_packet(const float4* __restrict__ nodes, const float4* __restrict__ tris, int root, Packet<K>& pk,
+                                             unsigned& n_nodes, unsigned& n_tris)
+{
+    StackCull stack;
+    int sp = 0;
+    int cur = root;
+    while (cur != LRC_SENTINEL) {
+        const float bmax = packet_bmax(pk);
+        while (cur >= 0) cur = inner_step_k<K, COUNT>(nodes, cur, pk, stack, sp, bmax, n_nodes);
+        if (cur != LRC_SENTINEL) {
+            leaf_test_k<K>(tris, cur, pk, n_tris);
+            cur = StackOps<StackCull>::pop(stack, sp, packet_bmax(pk), nullptr, 0);
+        }
+    }
+}
+
 // Stack-based closest-hit traversal.  VARIANT bit 0: 0 = one node (inner or leaf) per loop trip ("if-if"),
 // 1 = "while-while" -- run down inner nodes until a leaf (or the end) is reached, then test the leaf.
 // VARIANT bit 1: node records fetched with 256-bit loads.  VARIANT bit 2 (scan.cu): 32-register cap (64 warps per SM).
 // VARIANT bit 3: the first top_n nodes (heap order) are read from shared memory.
 // VARIANT bit 4: the first stack levels live in shared memory (StackShared).
 // VARIANT bit 5: 32-byte quantised node records (trace_loop_q; while-while only).
+// VARIANT bit 7: paired node records + packed FMA (trace_loop_p, node format 2; with or without bit 6).
 // VARIANT bit 6: stack entries carry their entry distance and are culled against the best hit at pop time (StackCull).
 template <int VARIANT, bool COUNT, class STACK>
 __device__ __forceinline__ void trace_loop(const float4* __restrict__ nodes, const float4* __restrict__ tris,
@@ -356,7 +566,10 @@ __device__ __forceinline__ void trace_ray(const float4* __restrict__ nodes, cons
                                           float oy, float oz, float dx, float dy, float dz, float& best_t,
                                           uint32_t& best_id, unsigned& n_nodes, unsigned& n_tris)
 {
-    if (VARIANT & 32) {
+    if (VARIANT & 128) {
+        if (VARIANT & 64) trace_loop_p<COUNT, StackCull>(nodes, tris, root, ox, oy, oz, dx, dy, dz, best_t, best_id, n_nodes, n_tris);
+        else trace_loop_p<COUNT, StackLocal>(nodes, tris, root, ox, oy, oz, dx, dy, dz, best_t, best_id, n_nodes, n_tris);
+    } else if (VARIANT & 32) {
         trace_loop_q<COUNT>(nodes, tris, nq, root, ox, oy, oz, dx, dy, dz, best_t, best_id, n_nodes, n_tris);
     } else if (VARIANT & 16) {
         StackShared st;

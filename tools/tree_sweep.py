@@ -30,7 +30,10 @@ def main():
     ap.add_argument("--quality", default="0,1")
     ap.add_argument("--variants", default="1,65")
     ap.add_argument("--leaf", default="2")
-    ap.add_argument("--radius", default="16")
+    ap.add_argument("--radius", default="8")
+    ap.add_argument("--formats", default="0", help="node formats: 0 = 64 B centre/half, 1 = 32 B 16-bit, 2 = 64 B paired (packed FMA)")
+    ap.add_argument("--persistent", default="0", help="0 / 1: persistent warps over 32-ray tiles")
+    ap.add_argument("--rpt", default="1", help="rays per thread (1, 2, 4); > 1 needs format 2")
     ap.add_argument("--poses", type=int, default=None)
     ap.add_argument("--tris", type=int, default=None)
     args = ap.parse_args()
@@ -48,9 +51,10 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     ref = None
     ints = lambda s: [int(x) for x in s.split(",")]
-    for q, leaf, rad in itertools.product(ints(args.quality), ints(args.leaf), ints(args.radius)):
+    for q, leaf, rad, fmt in itertools.product(ints(args.quality), ints(args.leaf), ints(args.radius), ints(args.formats)):
         if q == 0 and rad != ints(args.radius)[0]:
             continue
+        ctx.set_option("node_format", fmt)
         ctx.set_option("build_quality", q)
         ctx.set_option("leaf_size", leaf)
         ctx.set_option("ploc_radius", rad)
@@ -63,8 +67,12 @@ def main():
         torch.cuda.synchronize()
         build_ms = e0.elapsed_time(e1)
         info = ctx.bvh_info()
-        for var in ints(args.variants):
+        for var, pers, rpt in itertools.product(ints(args.variants), ints(args.persistent), ints(args.rpt)):
+            if rpt > 1 and (fmt != 2 or pers or var != ints(args.variants)[-1]):
+                continue
             ctx.set_option("variant", var)
+            ctx.set_option("persistent", pers)
+            ctx.set_option("rays_per_thread", rpt)
             ctx.set_counting(True)
             ctx.counters(reset=True)
             ctx.scan_enqueue(poses_d, intr, noise, bufs)
@@ -86,7 +94,7 @@ def main():
             if ref is None:
                 ref = sig
             rays = max(1, cnt["rays"])
-            print(json.dumps({"workload": args.workload, "quality": q, "leaf_size": leaf, "ploc_radius": rad if q else None, "variant": var,
+            print(json.dumps({"workload": args.workload, "quality": q, "leaf_size": leaf, "ploc_radius": rad if q else None, "node_format": fmt, "variant": var, "persistent": pers, "rays_per_thread": rpt,
                               "build_ms": round(build_ms, 3), "height": info["max_depth"], "sah": round(info["sah_cost"], 2),
                               "nodes_per_ray": round(cnt["nodes_visited"] / rays, 2), "tris_per_ray": round(cnt["tris_tested"] / rays, 2),
                               "trace_ms": round(float(np.mean(tr)), 4), "trace_ms_min": round(float(np.min(tr)), 4),
