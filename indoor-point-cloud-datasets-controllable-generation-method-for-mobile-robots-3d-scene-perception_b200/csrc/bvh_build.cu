@@ -436,6 +436,41 @@ __global__ void k_refit(int n, const int* __restrict__ parent_leaf, const int* _
     }
 }
 
+// ---- live-node compaction ---------------------------------------------------------------------------------------------
+// A subtree of <= leaf_size triangles is ONE leaf link in its parent, so the records of its inner nodes are never read --
+// with two-triangle leaves that is about half of the T-1 records, interleaved with the live ones: every 128 B line of the
+// bottom levels would carry one live record on average.  The builders therefore write their records to scratch, and
+// k_compact_nodes moves the live ones (root + nodes with more than leaf_size triangles) to consecutive slots in the same
+// order (siblings stay adjacent, subtrees stay contiguous) and rewrites the inner links: half the node footprint in L1 / L2
+// / HBM for the same tree.
+__global__ void k_live_flags_lbvh(int n_nodes, const int2* __restrict__ range, int leaf_max, unsigned* __restrict__ live)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_nodes) live[i] = (i == 0 || range[i].y > leaf_max) ? 1u : 0u;
+}
+
+__global__ void k_compact_nodes(int n_nodes, const float4* __restrict__ src, const unsigned* __restrict__ new_index,
+                                const unsigned* __restrict__ live, float4* __restrict__ dst, int format)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes || !live[i]) return;
+    const int64_t d = new_index[i];
+    if (format == 1) {
+        float4 a = src[2 * (int64_t)i], b = src[2 * (int64_t)i + 1];
+        const int l0 = __float_as_int(a.w), l1 = __float_as_int(b.w);
+        if (l0 >= 0) a.w = __int_as_float((int)new_index[l0]);
+        if (l1 >= 0) b.w = __int_as_float((int)new_index[l1]);
+        dst[2 * d] = a; dst[2 * d + 1] = b;
+    } else {
+        const float4* r = src + 4 * (int64_t)i;
+        float4 k = r[3];
+        const int l0 = __float_as_int(k.x), l1 = __float_as_int(k.y);
+        if (l0 >= 0) k.x = __int_as_float((int)new_index[l0]);
+        if (l1 >= 0) k.y = __int_as_float((int)new_index[l1]);
+        dst[4 * d] = r[0]; dst[4 * d + 1] = r[1]; dst[4 * d + 2] = r[2]; dst[4 * d + 3] = k;
+    }
+}
+
 // T == 1: a root record whose two links both point at the only leaf (testing it twice is harmless)
 __global__ void k_single_leaf_root(const float4* leaf_lo, const float4* leaf_hi, float4* nodes_out, BuildMeta* meta, int format,
                                    NodeQ nq)
@@ -545,6 +580,7 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
     // whatever stream that ran on
     if (ctx->scratch_event) LRC_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->scratch_event, 0));
     const int quality = (T > 2) ? (int)ctx->opt_build_quality : 0;
+    const bool compact = ctx->opt_compact_nodes != 0;
 
     // ---- carve the build scratch ----
     const int nb = (int)((T + RS_TILE - 1) / RS_TILE);
@@ -559,6 +595,8 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
     size_t o_pl = carve(sizeof(int) * T), o_pn = carve(sizeof(int) * n_nodes);
     size_t o_ch = carve(sizeof(int2) * n_nodes), o_fl = carve(sizeof(int) * n_nodes);
     size_t o_rg = carve(sizeof(int2) * n_nodes);
+    size_t o_tmpn = carve(compact ? sizeof(float4) * (format == 1 ? 2 : 4) * (size_t)n_nodes : 16);       // records before the live-node compaction
+    size_t o_live = carve(sizeof(unsigned) * (size_t)n_nodes), o_newi = carve(sizeof(unsigned) * ((size_t)n_nodes + 16));
     // PLOC only: two cluster buffers, per-iteration bookkeeping, subtree positions (o_ch / o_rg hold left|right and
     // left-count|start; the key buffer k1 is free after the sort)
     size_t o_cid0 = 0, o_cid1 = 0, o_clo0 = 0, o_clo1 = 0, o_chi0 = 0, o_chi1 = 0, o_nn = 0, o_role = 0, o_bsum = 0, o_sl = 0;
@@ -582,6 +620,9 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
     int* parent_leaf = (int*)(base + o_pl); int* parent_node = (int*)(base + o_pn);
     int2* children = (int2*)(base + o_ch); int* flags = (int*)(base + o_fl);
     int2* range = (int2*)(base + o_rg);
+    float4* tmp_nodes = compact ? (float4*)(base + o_tmpn) : ctx->nodes;      // where the builders write their records
+    unsigned* live = (unsigned*)(base + o_live);
+    unsigned* new_index = (unsigned*)(base + o_newi);
 
     const int TB = 256;
     const unsigned gT = (unsigned)((T + TB - 1) / TB);
@@ -661,8 +702,8 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
         LRC_CUDA(ctx, cudaMemsetAsync(parent_node + (T - 2), 0xff, sizeof(int), stream));      // the root (last node created) has no parent
         k_ploc_positions<<<(unsigned)((2 * T - 1 + TB - 1) / TB), TB, 0, stream>>>((int)T, tr, meta);
         LRC_CHECK_LAUNCH(ctx, "k_ploc_positions");
-        k_ploc_emit<<<(unsigned)((T - 1 + TB - 1) / TB), TB, 0, stream>>>((int)T, tr, leaf_lo, leaf_hi, ctx->nodes, format, nq,
-                                                                          (int)ctx->opt_leaf_size, meta);
+        k_ploc_emit<<<(unsigned)((T - 1 + TB - 1) / TB), TB, 0, stream>>>((int)T, tr, leaf_lo, leaf_hi, tmp_nodes, format, nq,
+                                                                          (int)ctx->opt_leaf_size, meta, live);
         LRC_CHECK_LAUNCH(ctx, "k_ploc_emit");
         k_tri_records<<<gT, TB, 0, stream>>>(verts, tris, T, vin, tr.start_leaf, ctx->tris);
         LRC_CHECK_LAUNCH(ctx, "k_tri_records");
@@ -678,9 +719,27 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
             LRC_CHECK_LAUNCH(ctx, "k_hierarchy");
             LRC_CUDA(ctx, cudaMemsetAsync(flags, 0, sizeof(int) * n_nodes, stream));
             k_refit<<<gT, TB, 0, stream>>>((int)T, parent_leaf, parent_node, children, leaf_lo, leaf_hi, node_lo, node_hi, flags,
-                                           ctx->nodes, meta, format, nq, range, (int)ctx->opt_leaf_size);
+                                           tmp_nodes, meta, format, nq, range, (int)ctx->opt_leaf_size);
             LRC_CHECK_LAUNCH(ctx, "k_refit");
+            if (compact) {
+                k_live_flags_lbvh<<<gN, TB, 0, stream>>>((int)n_nodes, range, (int)ctx->opt_leaf_size, live);
+                LRC_CHECK_LAUNCH(ctx, "k_live_flags_lbvh");
+            }
         }
+    }
+    int64_t n_live = n_nodes;
+    if (T > 1 && compact) {
+        // exclusive scan of the live flags = new record index; the total comes back with the build meta
+        LRC_CUDA(ctx, cudaMemcpyAsync(new_index, live, sizeof(unsigned) * (size_t)n_nodes, cudaMemcpyDeviceToDevice, stream));
+        k_rs_scan<<<1, 1024, 0, stream>>>(new_index, n_nodes);
+        LRC_CHECK_LAUNCH(ctx, "k_rs_scan");
+        k_compact_nodes<<<(unsigned)((n_nodes + TB - 1) / TB), TB, 0, stream>>>((int)n_nodes, tmp_nodes, new_index, live, ctx->nodes, format);
+        LRC_CHECK_LAUNCH(ctx, "k_compact_nodes");
+        unsigned tail[2];
+        LRC_CUDA(ctx, cudaMemcpyAsync(&tail[0], new_index + (n_nodes - 1), sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+        LRC_CUDA(ctx, cudaMemcpyAsync(&tail[1], live + (n_nodes - 1), sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+        LRC_CUDA(ctx, cudaStreamSynchronize(stream));
+        n_live = (int64_t)tail[0] + tail[1];
     }
     LRC_CUDA(ctx, cudaMemcpyAsync(&hm, meta, sizeof hm, cudaMemcpyDeviceToHost, stream));
     LRC_CUDA(ctx, cudaStreamSynchronize(stream));
@@ -701,7 +760,7 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
 
     lrc_bvh_info& inf = ctx->info;
     inf.num_tris = T;
-    inf.num_nodes = n_nodes;
+    inf.num_nodes = n_live;
     inf.max_depth = hm.height;
     for (int k = 0; k < 3; ++k) { inf.scene_min[k] = slo[k]; inf.scene_max[k] = shi[k]; }
     inf.box_pad = pad;
@@ -710,7 +769,7 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
         ctx->root_area = 2.0 * ((double)ex * ey + (double)ey * ez + (double)ez * ex);
         inf.sah_cost = -1.f;   // computed on demand by lrc_bvh_get_info
     }
-    inf.bytes_nodes = (int64_t)sizeof(float4) * (format == 1 ? 2 : 4) * n_nodes;
+    inf.bytes_nodes = (int64_t)sizeof(float4) * (format == 1 ? 2 : 4) * n_live;
     inf.bytes_tris = (int64_t)sizeof(float4) * 3 * T;
     if (hm.height + 1 >= LRC_STACK_DEPTH && quality) {
         // a PLOC tree has no height bound; the radix tree's is the key length -- rebuild with it rather than fail

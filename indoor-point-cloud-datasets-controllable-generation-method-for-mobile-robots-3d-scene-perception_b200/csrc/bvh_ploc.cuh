@@ -321,7 +321,8 @@ __device__ __forceinline__ int ploc_link(const PlocTree& tr, int child, int leaf
 }
 
 __global__ void k_ploc_emit(int T, PlocTree tr, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
-                            float4* __restrict__ nodes_out, int format, NodeQ nq, int leaf_max, BuildMeta* meta)
+                            float4* __restrict__ nodes_out, int format, NodeQ nq, int leaf_max, BuildMeta* meta,
+                            unsigned* __restrict__ live)
 {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= T - 1) return;
@@ -339,6 +340,7 @@ __global__ void k_ploc_emit(int T, PlocTree tr, const float4* __restrict__ leaf_
     const int p = tr.parent_node[a];
     const int idx = p < 0 ? 0 : tr.start_node[p] + tr.cl[p] - 1 + (tr.right[p] == a ? 1 : 0);
     emit_node(nodes_out, idx, format, nq, l0, h0, l1, h1, k0, k1);
+    live[idx] = (p < 0 || __float_as_int(tr.lo[a].w) > leaf_max) ? 1u : 0u;      // dead: collapsed into a leaf link of an ancestor
     if (p < 0) {
         const float4 lo = tr.lo[a], hi = tr.hi[a];
         meta->root_lo[0] = lo.x; meta->root_lo[1] = lo.y; meta->root_lo[2] = lo.z;

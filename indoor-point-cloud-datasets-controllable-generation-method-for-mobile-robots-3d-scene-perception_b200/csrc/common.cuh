@@ -32,13 +32,14 @@ struct lrc_ctx {
     float4* tris = nullptr;       // T x 3 float4 (48 B records, Morton order): (v0|orig id) (e1|0) (e2|0)
     uint32_t* labels = nullptr;   // T, original triangle order
     int64_t opt_leaf_size = 2;    // triangles per leaf built by the NEXT lrc_set_mesh (1..8); 2 measured best
-    int64_t opt_build_quality = 1;   // builder of the NEXT lrc_set_mesh: 0 = LBVH (Karras radix tree), 1 = PLOC (bvh_ploc.cuh)
+    int64_t opt_build_quality = 0;   // builder of the NEXT lrc_set_mesh: 0 = LBVH (Karras radix tree), 1 = PLOC (bvh_ploc.cuh)
     int64_t opt_ploc_radius = 16;    // PLOC search radius (clusters before / after in Morton order), 1..32
     int build_quality = 0;        // builder of the tree that is resident now
     int ploc_iterations = 0;
     int root = 0;                 // node record the traversal starts at
     int* h_pin = nullptr;         // small page-locked mailbox (PLOC merge counts)
-    int64_t opt_node_format = 0;  // format the NEXT lrc_set_mesh builds: 0 = 64 B float boxes, 1 = 32 B 16-bit boxes
+    int64_t opt_node_format = 2;  // format the NEXT lrc_set_mesh builds: 0 = 64 B float boxes, 1 = 32 B 16-bit boxes, 2 = 64 B paired boxes (packed FMA)
+    int64_t opt_compact_nodes = 0;   // 1: keep only the live node records (half the node footprint, +30 % build time, < 1 % traversal time)
     int node_format = 0;          // format of the tree that is resident now
     NodeQ nodeq = {};
     float4* top_table = nullptr;  // (2^LRC_TOP_LEVELS_MAX - 1) x 4 float4: copies of the top nodes in heap order
@@ -128,8 +129,8 @@ struct lrc_ctx {
     int num_sms = 148;
     int64_t opt_block = 128;            // threads per traversal block
     int64_t opt_chunk_rays = 1 << 26;   // rays per traversal/epilogue chunk (bounds scratch: 16 B per ray)
-    int64_t opt_variant = 1;            // traversal kernel variant: while-while loop (bit 2, the 32-register build, lost
-                                        // its edge once leaves hold two triangles: profiles/r01f_leaf_size_sweep.jsonl)
+    int64_t opt_variant = 65;           // traversal kernel variant: while-while loop + stack entries culled at pop time (bit 6);
+                                        // with node format 2 the packed-FMA loop (bit 7) is selected automatically
 };
 
 extern char g_lrc_global_err[512];

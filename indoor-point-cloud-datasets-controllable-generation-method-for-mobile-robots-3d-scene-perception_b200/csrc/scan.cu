@@ -205,13 +205,38 @@ constexpr int TRACE_THREADS = 128;
 // OUT_DENSE: write (t_hit, prim_id) per ray (cast_rays).  Otherwise, per ray, the float32 hit point + triangle id
 // (float4; id = MISS when the ray missed, was dropped or failed the range test), the incident angle, and per BLOCK
 // the number of kept rays (block_count) -- the first stage of the ordered compaction.
-// VARIANT bit 8 ("persistent"): the grid is sized to fill the machine once and every WARP walks over 32-ray tiles with a
-// static stride (tile = warp number + k * warps in the grid) -- no block-wide barrier parks finished warps behind the block's
-// slowest ray (ncu, round 1: 2.75 warps per issue slot stalled at the barrier), every resident warp always has a ray.  The
-// per-block keep counts the compaction needs are then accumulated with one atomicAdd per tile (integer adds commute, so the
-// counts -- and the output order -- stay deterministic); the launcher zeroes them first.
+// One ray of a k_trace launch: generate, traverse, frame arithmetic (or the dense t / id outputs).  Returns "kept".
 template <int MODE, bool COUNT, bool OUT_DENSE, int VARIANT>
-__global__ void __launch_bounds__(TRACE_THREADS, (VARIANT & 4) ? 16 : 12)   // 40 registers (48 warps per SM); VARIANT bit 2: 32 registers (64 warps)
+__device__ __forceinline__ bool trace_one(const RayGen& g, const FrameMath& fm, const float4* __restrict__ nodes,
+                                          const float4* __restrict__ tris, int64_t idx, int has_tris, float4* __restrict__ hp,
+                                          double* __restrict__ inc_out, float* __restrict__ t_hit, uint32_t* __restrict__ prim_id,
+                                          const float4* s_top, int top_n, int stack_levels, const NodeQ& nq, int root, unsigned& nn,
+                                          unsigned& nt, unsigned& nr, unsigned& nh)
+{
+    int64_t pose; int r;
+    Ray ray = gen_ray<MODE>(g, idx, pose, r);
+    float t = LRC_INF;
+    uint32_t id = LRC_MISS_ID;
+    if (ray.keep && has_tris) {
+        trace_ray<VARIANT, COUNT>(nodes, tris, s_top, top_n, stack_levels, nq, root, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, t, id, nn, nt);
+        nr += 1;
+        nh += id != LRC_MISS_ID;
+    }
+    if (OUT_DENSE) {
+        t_hit[idx] = t;
+        prim_id[idx] = id;
+        return false;
+    }
+    return frame_epilogue<MODE>(g, fm, idx, pose, r, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, t, id, hp, inc_out);
+}
+
+// VARIANT bit 8 ("persistent"): the grid is sized to fill the machine once and every WARP keeps fetching work -- one
+// 128-ray block of the compaction at a time (an atomic ticket per block), walked as tiles of 32 consecutive rays.  No
+// block-wide barrier parks finished warps behind the block's slowest ray (ncu: ~18 % of the resident warp-time is spent at
+// that barrier) and the tail of the launch is balanced at warp granularity.  The warp owns its whole block, so the keep
+// count is a plain store.
+template <int MODE, bool COUNT, bool OUT_DENSE, int VARIANT>
+__global__ void __launch_bounds__(TRACE_THREADS, (VARIANT & 4) ? 16 : (VARIANT & 512) ? 10 : 12)   // 40 registers (48 warps per SM); bit 2: 32 registers (64 warps); bit 9: 48 registers (40 warps)
 k_trace(RayGen g, FrameMath fm, const float4* __restrict__ nodes, const float4* __restrict__ tris, int64_t n, int has_tris,
         float4* __restrict__ hp, double* __restrict__ inc_out, unsigned* __restrict__ block_count, float* __restrict__ t_hit,
         uint32_t* __restrict__ prim_id, unsigned long long* counters, const float4* __restrict__ top_table, int top_n,
@@ -224,41 +249,33 @@ k_trace(RayGen g, FrameMath fm, const float4* __restrict__ nodes, const float4* 
         __syncthreads();
     }
     unsigned nn = 0, nt = 0, nr = 0, nh = 0;
-    const int64_t n_tiles = (n + 31) >> 5;
-    const int64_t tile_stride = (int64_t)gridDim.x * (blockDim.x >> 5);
-    int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (PERSIST && tile >= n_tiles) return;
-    do {
-    const int64_t idx = PERSIST ? (tile << 5) + lane_id() : (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool keep = false;
-    if (idx < n) {
-        int64_t pose; int r;
-        Ray ray = gen_ray<MODE>(g, idx, pose, r);
-        float t = LRC_INF;
-        uint32_t id = LRC_MISS_ID;
-        if (ray.keep && has_tris) {
-            trace_ray<VARIANT, COUNT>(nodes, tris, s_top, top_n, stack_levels, nq, root, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, t, id, nn, nt);
-            nr += 1;
-            nh += id != LRC_MISS_ID;
+    if (PERSIST) {
+        unsigned* ticket = reinterpret_cast<unsigned*>(counters + 4);
+        const unsigned tiles_per_block = 1u << tile_shift;
+        const unsigned n_blocks = (unsigned)((n + (32u << tile_shift) - 1) >> (5 + tile_shift));
+        for (;;) {
+            unsigned b = 0;
+            if (lane_id() == 0) b = atomicAdd(ticket, 1u);
+            b = __shfl_sync(0xffffffffu, b, 0);
+            if (b >= n_blocks) break;
+            unsigned kept = 0;
+            for (unsigned k = 0; k < tiles_per_block; ++k) {
+                const int64_t idx = (((int64_t)b << tile_shift) + k) * 32 + lane_id();
+                bool keep = false;
+                if (idx < n) keep = trace_one<MODE, COUNT, OUT_DENSE, VARIANT>(g, fm, nodes, tris, idx, has_tris, hp, inc_out, t_hit, prim_id, s_top, top_n, stack_levels, nq, root, nn, nt, nr, nh);
+                kept += __popc(__ballot_sync(0xffffffffu, keep));
+            }
+            if (!OUT_DENSE && lane_id() == 0) block_count[b] = kept;
         }
-        if (OUT_DENSE) {
-            t_hit[idx] = t;
-            prim_id[idx] = id;
-        } else {
-            keep = frame_epilogue<MODE>(g, fm, idx, pose, r, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, t, id, hp, inc_out);
-        }
-    }
-    if (!OUT_DENSE) {
-        if (PERSIST) {
-            const unsigned b = __ballot_sync(0xffffffffu, keep);
-            if (lane_id() == 0 && b) atomicAdd(&block_count[tile >> tile_shift], (unsigned)__popc(b));
-        } else {
+    } else {
+        const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        bool keep = false;
+        if (idx < n) keep = trace_one<MODE, COUNT, OUT_DENSE, VARIANT>(g, fm, nodes, tris, idx, has_tris, hp, inc_out, t_hit, prim_id, s_top, top_n, stack_levels, nq, root, nn, nt, nr, nh);
+        if (!OUT_DENSE) {
             const int c = __syncthreads_count(keep ? 1 : 0);
             if (threadIdx.x == 0) block_count[blockIdx.x] = (unsigned)c;
         }
     }
-    tile += tile_stride;
-    } while (PERSIST && tile < n_tiles);
     if (COUNT) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -562,8 +579,8 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_push(PushParams q, const __gri
 int ensure_counters(lrc_ctx* ctx)
 {
     if (!ctx->d_counters) {
-        LRC_CUDA(ctx, cudaMalloc((void**)&ctx->d_counters, 4 * sizeof(unsigned long long)));
-        LRC_CUDA(ctx, cudaMemset(ctx->d_counters, 0, 4 * sizeof(unsigned long long)));
+        LRC_CUDA(ctx, cudaMalloc((void**)&ctx->d_counters, 8 * sizeof(unsigned long long)));      // [0..3] work counters, [4] persistent-kernel ticket
+        LRC_CUDA(ctx, cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned long long)));
     }
     return LRC_OK;
 }
@@ -619,13 +636,12 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
     int tile_shift = 0;
     if (ctx->opt_persistent && (variant == 1 || variant == 65 || variant == 129 || variant == 193)) {
         variant |= 256;
-        const unsigned fill = (unsigned)(ctx->num_sms * 12 * (TRACE_THREADS / TB));      // blocks that are resident at once
+        if (ctx->opt_persistent == 2 && variant == 449) variant |= 512;
+        const unsigned fill = (unsigned)(ctx->num_sms * ((variant & 512) ? 10 : 12) * (TRACE_THREADS / TB));      // blocks that are resident at once
         if (grid > fill) grid = fill;
         tile_shift = TB == 128 ? 2 : TB == 64 ? 1 : 0;
-        if (block_count) {     // per-block keep counts are accumulated with atomics: start from zero
-            cudaError_t me = cudaMemsetAsync(block_count, 0, sizeof(unsigned) * (size_t)((n + TB - 1) / TB), stream);
-            if (me != cudaSuccess) return lrc_fail(ctx, LRC_ERR_CUDA, "cudaMemsetAsync(block counts): %s", cudaGetErrorString(me));
-        }
+        cudaError_t me = cudaMemsetAsync(ctx->d_counters + 4, 0, sizeof(unsigned long long), stream);      // the work ticket
+        if (me != cudaSuccess) return lrc_fail(ctx, LRC_ERR_CUDA, "cudaMemsetAsync(ticket): %s", cudaGetErrorString(me));
     }
     const int top_n = (variant & 8) ? (int)((1 << ctx->opt_top_levels) - 1) : 0;
     const int stack_levels = (variant & 16) ? (int)ctx->opt_stack_levels : 0;
@@ -650,6 +666,7 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
             case 321: LRC_LAUNCH_TRACE(true, 321); break;
             case 385: LRC_LAUNCH_TRACE(true, 385); break;
             case 449: LRC_LAUNCH_TRACE(true, 449); break;
+            case 961: LRC_LAUNCH_TRACE(true, 961); break;
             default: LRC_LAUNCH_TRACE(true, 3); break;
         }
     } else {
@@ -668,6 +685,7 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
             case 321: LRC_LAUNCH_TRACE(false, 321); break;
             case 385: LRC_LAUNCH_TRACE(false, 385); break;
             case 449: LRC_LAUNCH_TRACE(false, 449); break;
+            case 961: LRC_LAUNCH_TRACE(false, 961); break;
             default: LRC_LAUNCH_TRACE(false, 3); break;
         }
     }
@@ -1013,6 +1031,7 @@ extern "C" int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value)
         ctx->opt_build_quality = value;    // takes effect at the next lrc_set_mesh
         return LRC_OK;
     }
+    if (!strcmp(key, "compact_nodes")) { ctx->opt_compact_nodes = value != 0; return LRC_OK; }      // takes effect at the next lrc_set_mesh
     if (!strcmp(key, "ploc_radius")) {
         if (value < 1 || value > 32) return lrc_fail(ctx, LRC_ERR_INVALID, "ploc_radius must be in [1, 32]");
         ctx->opt_ploc_radius = value;
@@ -1046,7 +1065,11 @@ extern "C" int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value)
         ctx->opt_rays_per_thread = value;
         return LRC_OK;
     }
-    if (!strcmp(key, "persistent")) { ctx->opt_persistent = value != 0; return LRC_OK; }
+    if (!strcmp(key, "persistent")) {
+        if (value < 0 || value > 2) return lrc_fail(ctx, LRC_ERR_INVALID, "persistent must be 0, 1 or 2 (2 = 48-register build)");
+        ctx->opt_persistent = value;
+        return LRC_OK;
+    }
     if (!strcmp(key, "kernel_timing")) { ctx->opt_kernel_timing = value != 0; ctx->kt_used = 0; return LRC_OK; }
     if (!strcmp(key, "variant")) {
         if (value < 0 || (value > 3 && value != 5 && value != 13 && value != 21 && value != 65)) return lrc_fail(ctx, LRC_ERR_INVALID, "variant must be 0..3, 5, 13, 21 or 65");

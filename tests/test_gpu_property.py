@@ -12,16 +12,17 @@ MISS = 0xFFFFFFFF
 @settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 @given(seed=st.integers(0, 2**31 - 1), n_tri=st.sampled_from([1, 2, 3, 31, 33, 127, 129, 1000, 4097]),
        n_ray=st.sampled_from([0, 1, 31, 32, 33, 127, 128, 129, 1000]), scale=st.sampled_from([1e-3, 1.0, 250.0]),
-       flat=st.booleans(), node_format=st.sampled_from([0, 1, 2]), persistent=st.sampled_from([0, 1]), rpt=st.sampled_from([1, 2, 4]), leaf_size=st.sampled_from([1, 3, 4, 8]),
+       flat=st.booleans(), node_format=st.sampled_from([0, 1, 2]), persistent=st.sampled_from([0, 1, 2]), rpt=st.sampled_from([1, 2, 4]), compact=st.booleans(), leaf_size=st.sampled_from([1, 3, 4, 8]),
        quality=st.sampled_from([0, 1]), radius=st.sampled_from([1, 5, 16, 32]), variant=st.sampled_from([1, 65]))
 def test_random_soups_bvh_equals_exhaustive(engine, lrc, orc, seed, n_tri, n_ray, scale, flat, node_format, leaf_size, quality,
-                                            radius, variant, persistent, rpt):
+                                            radius, variant, persistent, rpt, compact):
     engine.ctx.set_option("node_format", node_format)          # 64 B float boxes / 32 B 16-bit boxes: identical results
     engine.ctx.set_option("leaf_size", leaf_size)              # 1..8 triangles per leaf: identical results
     engine.ctx.set_option("build_quality", quality)            # LBVH / PLOC: identical results
     engine.ctx.set_option("ploc_radius", radius)
     engine.ctx.set_option("variant", variant)                  # plain stack / stack entries culled at pop time
     engine.ctx.set_option("persistent", persistent)            # one block per 128 rays / persistent warps over 32-ray tiles
+    engine.ctx.set_option("compact_nodes", int(compact))        # dead node records kept / squeezed out: identical results
     engine.ctx.set_option("rays_per_thread", rpt)              # 1 / 2 / 4 adjacent rays per thread (format 2 only): identical results
     engine.ctx._mesh_key = None
     rng = np.random.default_rng(seed)
@@ -52,11 +53,12 @@ def test_random_soups_bvh_equals_exhaustive(engine, lrc, orc, seed, n_tri, n_ray
     scan = engine.last_scan.numpy()
     hit = pid != MISS
     assert np.array_equal(scan["prim_id"], pid[hit]) and np.array_equal(scan["ray_idx"], np.nonzero(hit)[0].astype(np.uint32))
-    engine.ctx.set_option("node_format", 0)
+    engine.ctx.set_option("node_format", 2)                     # back to the defaults
     engine.ctx.set_option("leaf_size", 2)
-    engine.ctx.set_option("build_quality", 1)
+    engine.ctx.set_option("build_quality", 0)
     engine.ctx.set_option("ploc_radius", 16)
-    engine.ctx.set_option("variant", 1)
+    engine.ctx.set_option("compact_nodes", 0)
+    engine.ctx.set_option("variant", 65)
     engine.ctx.set_option("persistent", 0)
     engine.ctx.set_option("rays_per_thread", 1)
     engine.ctx._mesh_key = None
