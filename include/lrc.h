@@ -182,7 +182,7 @@ int lrc_set_mesh_host(lrc_ctx* ctx, const float* h_verts, int64_t V, const int32
 typedef struct { unsigned char bytes[64]; } lrc_ipc_handle;
 typedef struct {
     int32_t n_targets;
-    int32_t reserved;
+    int32_t frame_capacity;  /* frame-offset slots of this rank's region (a scan of P frames writes P + 1); 0 = not checked */
     float* xyz[LRC_MAX_GATHER_TARGETS];
     uint32_t* label[LRC_MAX_GATHER_TARGETS];
     int64_t* frame_offset[LRC_MAX_GATHER_TARGETS];
@@ -218,6 +218,14 @@ typedef struct {
 } lrc_frame_stats;
 int lrc_frame_statistics(lrc_ctx* ctx, const float* xyz, const double* incident_deg, const int64_t* frame_offset,
                          int64_t P, lrc_frame_stats* out, void* stream);
+/* == the incident-angle lines of RaycastEngineCPU.lidar_intersect_mesh (raycast_engine_cpu.py:100-107) for points that are
+ *    already known: incident_deg[i] = degrees(arccos(|(p_i - c)_z / ||p_i - c|||)), float64, c = poses[frame(i)][:3, 3],
+ *    frame(i) from frame_offset (P + 1 entries; frame f owns [frame_offset[f], frame_offset[f + 1])).  Bit-identical to the
+ *    angles a scan produces for the same points; used after the multi-GPU exchange, which moves xyz + label only.
+ *    xyz: M x 3 float32, poses: P x 16 float64, all device.  frame_offset may carry a base: xyz[0] is absolute point
+ *    frame_offset[0]; M is an upper bound (a capacity), points at or beyond frame_offset[P] are left untouched. */
+int lrc_incident_angles(lrc_ctx* ctx, const float* xyz, const int64_t* frame_offset, int64_t P, const double* poses, int64_t M,
+                        double* incident_deg, void* stream);
 /* == the vertex records S3DISSimScene._save_labeled_ply writes with struct.pack per point
  *    (containers/s3dis_sim_scene.py:634-641): M x 19 bytes, little endian, '<fff BBB HH' =
  *    x y z | red green blue | sem ins.  label = sem | ins << 16 (NULL: both 0, the reference's default labels,
@@ -276,6 +284,12 @@ int lrc_set_counting(lrc_ctx* ctx, int enabled);
 int lrc_counters(lrc_ctx* ctx, lrc_counters_t* h_out, int reset, void* stream);
 /* Number of kernel launches issued by this context since creation (for bench.py's gpu_launches). */
 int64_t lrc_launch_count(const lrc_ctx* ctx);
+/* Small integers about the context, by name: "scratch_bytes" (grow-only scan/build scratch currently allocated),
+ * "bvh_bytes", "node_format", "build_quality", "ploc_iterations" (of the resident tree), and the generation counters
+ * "mesh_generation" / "nn_generation" / "collision_generation", which lrc_set_mesh / lrc_nn_index_build /
+ * lrc_collision_index_build bump: the context holds ONE index of each kind, so a host object that built one remembers the
+ * generation and rebuilds (or refuses) when somebody else has re-targeted the slot since. */
+int lrc_get_stat(lrc_ctx* ctx, const char* key, int64_t* h_value);
 /* Device time of the traversal kernel (k_trace) and of the ordered compaction (k_scan_counts + k_compact) of the LAST
  * scan call, from CUDA events recorded on the streams those kernels were launched on; summed over the call's pose
  * chunks (*h_launches = number of chunks = k_trace launches).  Requires lrc_set_option(ctx, "kernel_timing", 1)
@@ -284,10 +298,17 @@ int lrc_kernel_times(lrc_ctx* ctx, double* h_trace_ms, double* h_compact_ms, int
 /* Tuning knobs (defaults are the measured best; none of them changes a result bit):
  *   "variant"       traversal kernel: bit 0 while-while loop, bit 1 256-bit node loads, bit 2 32-register build,
  *                   bit 3 top of the tree in shared memory ("top_levels" 1..8), bit 4 stack in shared memory
- *                   ("stack_levels" 1..48); accepted values 0..3, 1 (default), 5, 13, 21
- *   "leaf_size"     triangles per leaf built by the NEXT lrc_set_mesh, 1..8 (default 2): subtrees of the radix tree with
- *                   at most that many Morton-consecutive triangles are tested as one leaf
- *   "node_format"   record format built by the NEXT lrc_set_mesh: 0 = 64 B float boxes (default), 1 = 32 B 16-bit boxes
+ *                   ("stack_levels" 1..48), bit 6 stack entries culled against the best hit at pop time; accepted values
+ *                   0..3, 5, 13, 21, 65 (default).  Node format 2 always runs the packed-FMA loop (with / without bit 6).
+ *   "leaf_size"     triangles per leaf built by the NEXT lrc_set_mesh, 1..8 (default 2): subtrees with at most that many
+ *                   consecutive triangles are tested as one leaf
+ *   "node_format"   record format built by the NEXT lrc_set_mesh: 0 = 64 B float boxes, 1 = 32 B 16-bit boxes,
+ *                   2 = 64 B paired boxes for the two-wide FP32 FMA of sm_100 (default)
+ *   "build_quality" builder of the NEXT lrc_set_mesh: 0 = LBVH (Karras radix tree, default), 1 = PLOC (locally-ordered
+ *                   clustering with "ploc_radius" 1..32, default 16): ~12 % fewer node fetches per ray, 2x the build time
+ *   "compact_nodes" 1: squeeze the never-read records of collapsed subtrees out of the node array (half the node bytes)
+ *   "rays_per_thread" 1 (default), 2, 4: adjacent rays per thread of the scan kernels (format 2 only; measured slower)
+ *   "persistent"    1 / 2: persistent warps that fetch 128-ray blocks by ticket instead of one block per 128 rays
  *   "block"         threads per traversal block (32 / 64 / 128)
  *   "chunk_rays"    rays per traversal chunk (bounds the 24 B/ray scratch)
  *   "gather_chunks", "gather_ramp", "push_blocks"   pose chunks / short first chunk / exchange blocks of the all-gather

@@ -51,7 +51,7 @@ class IpcHandle(C.Structure):          # lrc_ipc_handle
 
 
 class Gather(C.Structure):             # lrc_gather
-    _fields_ = [("n_targets", C.c_int32), ("reserved", C.c_int32), ("xyz", C.c_void_p * 16), ("label", C.c_void_p * 16),
+    _fields_ = [("n_targets", C.c_int32), ("frame_capacity", C.c_int32), ("xyz", C.c_void_p * 16), ("label", C.c_void_p * 16),
                 ("frame_offset", C.c_void_p * 16), ("point_base", C.c_int64), ("frame_base", C.c_int64), ("capacity", C.c_int64)]
 
 
@@ -96,6 +96,7 @@ SYMBOLS = {
     "lrc_gen_rays_single_axis": (_i32, [_vp, _vp, _i64, C.POINTER(SingleAxis), _vp, _vp]),
     "lrc_gen_rays_dual_axis": (_i32, [_vp, _vp, _i64, C.POINTER(DualAxis), C.POINTER(Noise), _vp, _vp, _vp]),
     "lrc_frame_statistics": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "lrc_incident_angles": (_i32, [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "lrc_pack_ply_records": (_i32, [_vp, _vp, _vp, _vp, _vp, C.c_uint32, _i64, _vp, _vp]),
     "lrc_nn_index_build": (_i32, [_vp, _vp, _i64, _dbl, _vp]),
     "lrc_nn_query": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -108,6 +109,7 @@ SYMBOLS = {
     "lrc_launch_count": (_i64, [_vp]),
     "lrc_set_option": (_i32, [_vp, C.c_char_p, _i64]),
     "lrc_default_l2_persist": (_i32, []),
+    "lrc_get_stat": (_i32, [_vp, C.c_char_p, C.POINTER(_i64)]),
     "lrc_kernel_times": (_i32, [_vp, C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(C.c_int32)]),
 }
 

@@ -68,17 +68,25 @@ def mesh_arrays(mesh):
 
 
 def mesh_fingerprint(mesh) -> tuple:
-    """Cheap identity of a mesh for the BVH cache: sizes plus a CRC of a strided sample of the data."""
+    """Content identity of a mesh for the BVH cache: sizes, dtypes and a CRC-32 of the COMPLETE vertex, index and label
+    buffers (about 6 ms per million triangles).  The reference rebuilds its scene on every call
+    (raycast_engine_cpu.py:46-47), so reusing a BVH is only legal when nothing changed -- an in-place edit of one
+    vertex or one label must be seen, which a sampled checksum cannot promise.  Callers that want to skip even this
+    pass pin the mesh explicitly (``Context.pin_mesh`` / ``RaycastEngineGPU.set_mesh``)."""
     if isinstance(mesh, (tuple, list)):
         v, f = np.asarray(mesh[0]), np.asarray(mesh[1])
+        lab = mesh[2] if len(mesh) > 2 else None
     else:
         v, f = np.asarray(mesh.vertices), np.asarray(mesh.triangles)
-    sv = max(1, v.shape[0] // 4096)
-    sf = max(1, f.shape[0] // 4096)
-    crc = zlib.crc32(np.ascontiguousarray(v[::sv]).tobytes())
-    crc = zlib.crc32(np.ascontiguousarray(f[::sf]).tobytes(), crc)
-    crc = zlib.crc32(np.ascontiguousarray(v[-1:]).tobytes(), crc)
-    return (id(mesh), v.shape[0], f.shape[0], crc)
+        lab = getattr(mesh, "triangle_labels", None)
+    crc = zlib.crc32(np.ascontiguousarray(v).data)
+    crc = zlib.crc32(np.ascontiguousarray(f).data, crc)
+    n_lab = -1
+    if lab is not None:
+        lab = np.asarray(lab)
+        n_lab = int(lab.shape[0])
+        crc = zlib.crc32(np.ascontiguousarray(lab).data, crc)
+    return (v.shape, str(v.dtype), f.shape, str(f.dtype), n_lab, crc)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -207,7 +215,7 @@ class Context:
         nat.check(None, self._lib.lrc_create(self.device_index, C.byref(h)))
         self._h = h
         self._mesh_key = None
-        self._mesh_refs = None
+        self._pinned = None               # the mesh object whose BVH is resident and trusted without hashing (pin_mesh)
         self.num_tris = 0
         self.has_labels = False
 
@@ -237,6 +245,13 @@ class Context:
     def set_option(self, key: str, value: int) -> None:
         nat.check(self._h, self._lib.lrc_set_option(self._h, key.encode(), int(value)))
 
+    def stat(self, key: str) -> int:
+        """``lrc_get_stat``: scratch_bytes, bvh_bytes, node_format, build_quality, ploc_iterations and the generation
+        counters of the context's single mesh / NN index / collision index slots."""
+        v = C.c_int64(0)
+        nat.check(self._h, self._lib.lrc_get_stat(self._h, key.encode(), C.byref(v)))
+        return int(v.value)
+
     def default_l2_persist(self) -> int:
         """The library's default for option ``l2_persist`` (percent of the maximum persisting-L2 set-aside)."""
         return int(self._lib.lrc_default_l2_persist())
@@ -250,6 +265,8 @@ class Context:
     # ---- scene ----
     def set_mesh_arrays(self, verts, tris, labels=None) -> None:
         """Upload float32 vertices / int32 indices / uint32 labels and build the LBVH on the GPU."""
+        self._mesh_key = None              # whatever happens below, the resident BVH is no longer the cached mesh's
+        self._pinned = None
         with torch.cuda.device(self.device):
             v = self._dev(verts, torch.float32).reshape(-1, 3)
             f = self._dev(tris, torch.int32).reshape(-1, 3)
@@ -262,17 +279,39 @@ class Context:
             nat.check(self._h, self._lib.lrc_set_mesh(self._h, _ptr(v), v.shape[0], _ptr(f), f.shape[0], _ptr(lab), self._stream()))
             self.num_tris = int(f.shape[0])
             self.has_labels = lab is not None
-            self._mesh_key = None
 
     def set_mesh(self, mesh, cache: bool = True) -> bool:
-        """Build (or reuse) the BVH of ``mesh``.  Returns True when a build happened."""
+        """Build (or reuse) the BVH of ``mesh``.  Returns True when a build happened.
+
+        ``cache=True`` reuses the resident BVH when the mesh is the pinned object (no hashing, see ``pin_mesh``) or when
+        its full-content fingerprint equals the resident one; ``cache=False`` always rebuilds, like the reference."""
+        if cache and self._pinned is not None and mesh is self._pinned:
+            return False
         key = mesh_fingerprint(mesh) if cache else None
-        if cache and key == self._mesh_key and self._mesh_key is not None:
+        if cache and self._mesh_key is not None and key == self._mesh_key:
             return False
         v, f, lab = mesh_arrays(mesh)
         self.set_mesh_arrays(v, f, lab)
         self._mesh_key = key
         return True
+
+    def pin_mesh(self, mesh) -> bool:
+        """Build the BVH of ``mesh`` (unless its content is already resident) and trust this OBJECT from now on: later
+        ``set_mesh(mesh)`` calls with the same object return at once, without reading its arrays.  The caller promises
+        not to edit the arrays in place; ``unpin_mesh()`` (or any other mesh) ends the promise."""
+        self._pinned = None
+        built = self.set_mesh(mesh, cache=True)
+        self._pinned = mesh
+        return built
+
+    def unpin_mesh(self) -> None:
+        self._pinned = None
+
+    def invalidate_mesh(self) -> None:
+        """Forget the pinned object and the cached fingerprint: the next ``set_mesh`` rebuilds (needed after changing a
+        build option such as ``leaf_size`` / ``node_format`` / ``build_quality``)."""
+        self._pinned = None
+        self._mesh_key = None
 
     def bvh_info(self) -> dict:
         info = nat.BvhInfo()
@@ -455,6 +494,8 @@ class Context:
             if isinstance(a, torch.Tensor):
                 a = a.numpy()
             return np.ascontiguousarray(a, dtype=dt)
+        self._mesh_key = None
+        self._pinned = None
         v = as_np(verts, np.float32).reshape(-1, 3)
         f = as_np(tris, np.int32).reshape(-1, 3)
         lab = None if labels is None else as_np(labels, np.int32 if (isinstance(labels, torch.Tensor) or labels.dtype == np.int32) else np.uint32).reshape(-1)
@@ -463,7 +504,6 @@ class Context:
                                                            None if lab is None else C.c_void_p(lab.ctypes.data)))
         self.num_tris = int(f.shape[0])
         self.has_labels = lab is not None
-        self._mesh_key = None
 
     # ---- get_rays ----
     def gen_rays(self, poses, intr, noise: Optional[NoiseConfig] = None):

@@ -548,6 +548,7 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
     cudaStream_t stream = (cudaStream_t)stream_;
     LRC_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->has_mesh = false;
+    ctx->mesh_generation++;
     ctx->T = T;
     ctx->V = V;
     ctx->has_labels = tri_label != nullptr;
@@ -556,6 +557,9 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
         ctx->has_mesh = true;
         return LRC_OK;
     }
+    // nodes, triangles, labels and the build scratch (carved out of ctx->scratch) are all read or written by scans:
+    // order this build after the last scan, whatever stream that ran on
+    if (ctx->scratch_event) LRC_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->scratch_event, 0));
     const int64_t n_nodes = T > 1 ? T - 1 : 1;
     const int format = (int)ctx->opt_node_format;
     {
@@ -576,9 +580,6 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
     if (tri_label) LRC_CUDA(ctx, cudaMemcpyAsync(ctx->labels, tri_label, sizeof(uint32_t) * T, cudaMemcpyDeviceToDevice, stream));
     else LRC_CUDA(ctx, cudaMemsetAsync(ctx->labels, 0, sizeof(uint32_t) * T, stream));
 
-    // the build scratch is carved out of ctx->scratch, which scans use as well: order this build after the last scan,
-    // whatever stream that ran on
-    if (ctx->scratch_event) LRC_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->scratch_event, 0));
     const int quality = (T > 2) ? (int)ctx->opt_build_quality : 0;
     const bool compact = ctx->opt_compact_nodes != 0;
 

@@ -26,6 +26,7 @@ struct lrc_ctx {
 
     // ---- scene (owned) ----
     bool has_mesh = false;
+    int64_t mesh_generation = 0;  // bumped by every lrc_set_mesh
     bool has_labels = false;
     int64_t T = 0, V = 0;
     float4* nodes = nullptr;      // num_nodes x 4 float4 (64 B records)
@@ -85,6 +86,7 @@ struct lrc_ctx {
         uint32_t* label[LRC_MAX_GATHER];
         int64_t* frame_offset[LRC_MAX_GATHER];
         int64_t point_base = 0, frame_base = 0, capacity = 0;
+        int64_t frame_capacity = 0;
     } gather;
     int64_t opt_gather_chunks = 4;
     int64_t opt_gather_ramp = 1;        // first gather chunk = regular chunk / ramp
@@ -92,6 +94,7 @@ struct lrc_ctx {
 
     // ---- planner support (plan.cu): binned vertex index ----
     bool ci_ready = false;
+    int64_t ci_generation = 0;    // bumped by every lrc_collision_index_build: host objects notice that the slot was re-targeted
     int64_t ci_V = 0;
     void* ci_meta = nullptr; size_t ci_meta_bytes = 0;
     void* ci_start = nullptr; size_t ci_start_bytes = 0;
@@ -102,6 +105,7 @@ struct lrc_ctx {
 
     // ---- 1-NN label transfer (nn.cu): binned annotated points ----
     bool nn_ready = false;
+    int64_t nn_generation = 0;    // bumped by every lrc_nn_index_build
     int64_t nn_n = 0;
     void* nn_meta = nullptr; size_t nn_meta_bytes = 0;
     void* nn_start = nullptr; size_t nn_start_bytes = 0;

@@ -156,6 +156,7 @@ extern "C" int lrc_nn_index_build(lrc_ctx* ctx, const double* ref_pts, int64_t n
     LRC_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t stream = (cudaStream_t)stream_;
     ctx->nn_ready = false;
+    ctx->nn_generation++;
     ctx->nn_n = n;
     ctx->nn_nb[0] = ctx->nn_nb[1] = ctx->nn_nb[2] = 0;
     if (n == 0) { ctx->nn_ready = true; return LRC_OK; }

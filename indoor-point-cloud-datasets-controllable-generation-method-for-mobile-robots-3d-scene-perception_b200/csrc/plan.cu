@@ -202,6 +202,7 @@ extern "C" int lrc_collision_index_build(lrc_ctx* ctx, const double* verts, int6
     LRC_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t stream = (cudaStream_t)stream_;
     ctx->ci_ready = false;
+    ctx->ci_generation++;
     ctx->ci_nbx = ctx->ci_nby = 0;
     ctx->ci_V = V;
     if (V == 0) { ctx->ci_ready = true; return LRC_OK; }

@@ -135,6 +135,49 @@ k_pack_ply(const float* __restrict__ xyz, const uint32_t* __restrict__ label, co
 
 }  // namespace
 
+// ---- incident angles from (point, pose) ----------------------------------------------------------------------------------
+// The reference's "incident angle" is a pure function of the float32 hit point and the frame's sensor position
+// (raycast_engine_cpu.py:95-107): degrees(arccos(|dz / dist|)) with dist = ||p - c|| in float64.  The multi-GPU exchange
+// therefore moves xyz + label only (16 B per point instead of 24) and every rank recomputes the angles of the gathered
+// cloud on arrival -- same operations in the same order as the scan's own epilogue (scan.cu frame_epilogue), so the bits
+// are identical.  One thread per point; the frame of a point is found by bisection of frame_offset.
+namespace {
+__global__ void k_incident_from_points(const float* __restrict__ xyz, const int64_t* __restrict__ frame_offset, int64_t P,
+                                       const double* __restrict__ poses, int64_t M, double* __restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    // offsets may carry a base (a rank's region of the gather buffer starts at rank * capacity): point i of xyz is
+    // absolute point frame_offset[0] + i, and the cloud ends at frame_offset[P] whatever upper bound M the caller gave
+    const int64_t ia = i + frame_offset[0];
+    if (ia >= frame_offset[P]) return;
+    int64_t lo = 0, hi = P;                     // largest f with frame_offset[f] <= ia
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (frame_offset[mid] <= ia) lo = mid; else hi = mid;
+    }
+    const double* Mx = poses + 16 * lo;
+    const double cx = Mx[3], cy = Mx[7], cz = Mx[11];
+    const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    const double ddx = __dsub_rn((double)x, cx), ddy = __dsub_rn((double)y, cy), ddz = __dsub_rn((double)z, cz);
+    const double dist = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz)));
+    out[i] = __dmul_rn(acos(fabs(__ddiv_rn(ddz, dist))), 180.0 / 3.141592653589793);
+}
+}  // namespace
+
+extern "C" int lrc_incident_angles(lrc_ctx* ctx, const float* xyz, const int64_t* frame_offset, int64_t P, const double* poses,
+                                   int64_t M, double* incident_deg, void* stream)
+{
+    if (!ctx) return lrc_fail(nullptr, LRC_ERR_INVALID, "lrc_incident_angles: ctx is NULL");
+    if (M < 0 || P < 0 || (M > 0 && (!xyz || !frame_offset || !poses || !incident_deg || P == 0)))
+        return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_incident_angles: bad arguments");
+    LRC_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (M == 0) return LRC_OK;
+    k_incident_from_points<<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(xyz, frame_offset, P, poses, M, incident_deg);
+    LRC_CHECK_LAUNCH(ctx, "k_incident_from_points");
+    return LRC_OK;
+}
+
 extern "C" int lrc_frame_statistics(lrc_ctx* ctx, const float* xyz, const double* incident_deg, const int64_t* frame_offset,
                                     int64_t P, lrc_frame_stats* out, void* stream_)
 {

@@ -716,6 +716,8 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
     if ((rc = ensure_counters(ctx))) return rc;
     const bool gather = ctx->gather.n > 0;
     if (gather && ctx->gather.capacity < total) return lrc_fail(ctx, LRC_ERR_CAPACITY, "lrc_set_gather: capacity is smaller than the number of rays");
+    if (gather && ctx->gather.frame_capacity > 0 && P + 1 > ctx->gather.frame_capacity)
+        return lrc_fail(ctx, LRC_ERR_CAPACITY, "lrc_set_gather: frame_capacity is smaller than the number of frames + 1");
     if (total == 0) {
         LRC_CUDA(ctx, cudaMemsetAsync(out->frame_offset, 0, sizeof(int64_t) * (P + 1), stream));
         return LRC_OK;
@@ -723,6 +725,7 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
     // chunk by whole frames: bounded scratch (24 B per ray per slot) and, with gather targets, overlap
     int64_t frames_per_chunk = ctx->opt_chunk_rays / N;
     if (frames_per_chunk < 1) frames_per_chunk = 1;
+    if (frames_per_chunk > P) frames_per_chunk = P;   // size the scratch by the largest REAL chunk (a one-frame call must not reserve 2^26 rays)
     if (MODE == MODE_RAYS) frames_per_chunk = P;   // a single explicit frame
     if (gather && MODE != MODE_RAYS && ctx->opt_gather_chunks > 1) {
         const int64_t want = (P + ctx->opt_gather_chunks - 1) / ctx->opt_gather_chunks;
@@ -859,6 +862,8 @@ int fill_single(lrc_ctx* ctx, const lrc_single_axis* s, const double* poses, Ray
     int rc = lrc_grow(ctx, (void**)&ctx->tables, &ctx->tables_bytes, sizeof(double) * (n_tab + s->H));
     if (rc) return rc;
     double* vdeg = ctx->tables + n_tab;
+    // the tables are shared by every scan of this context: a scan still running on another stream must finish with them first
+    if (ctx->scratch_event) LRC_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->scratch_event, 0));
     if (s->h_vertical_deg)
         LRC_CUDA(ctx, cudaMemcpyAsync(vdeg, s->h_vertical_deg, sizeof(double) * s->H, cudaMemcpyHostToDevice, stream));
     const int n = s->W + s->H;
@@ -980,6 +985,20 @@ extern "C" int lrc_counters(lrc_ctx* ctx, lrc_counters_t* h_out, int reset, void
     LRC_CUDA(ctx, cudaStreamSynchronize(stream));
     h_out->rays = h[0]; h_out->nodes_visited = h[1]; h_out->tris_tested = h[2]; h_out->hits = h[3];
     return LRC_OK;
+}
+
+extern "C" int lrc_get_stat(lrc_ctx* ctx, const char* key, int64_t* h_value)
+{
+    if (!ctx || !key || !h_value) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_get_stat: NULL argument");
+    if (!strcmp(key, "scratch_bytes")) { *h_value = (int64_t)(ctx->scratch_bytes + ctx->scratch2_bytes); return LRC_OK; }
+    if (!strcmp(key, "bvh_bytes")) { *h_value = (int64_t)ctx->bvh_bytes; return LRC_OK; }
+    if (!strcmp(key, "build_quality")) { *h_value = ctx->build_quality; return LRC_OK; }
+    if (!strcmp(key, "ploc_iterations")) { *h_value = ctx->ploc_iterations; return LRC_OK; }
+    if (!strcmp(key, "node_format")) { *h_value = ctx->node_format; return LRC_OK; }
+    if (!strcmp(key, "nn_generation")) { *h_value = ctx->nn_generation; return LRC_OK; }
+    if (!strcmp(key, "collision_generation")) { *h_value = ctx->ci_generation; return LRC_OK; }
+    if (!strcmp(key, "mesh_generation")) { *h_value = ctx->mesh_generation; return LRC_OK; }
+    return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_get_stat: unknown key '%s'", key);
 }
 
 extern "C" int lrc_kernel_times(lrc_ctx* ctx, double* h_trace_ms, double* h_compact_ms, int32_t* h_launches)
@@ -1415,11 +1434,12 @@ extern "C" int lrc_set_gather(lrc_ctx* ctx, const lrc_gather* h_targets)
     for (int k = 0; k < h_targets->n_targets; ++k)
         if (!h_targets->xyz[k] || !h_targets->label[k] || !h_targets->frame_offset[k])
             return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_gather: every target needs xyz, label and frame_offset");
-    if (h_targets->point_base < 0 || h_targets->frame_base < 0 || h_targets->capacity < 0) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_gather: negative base");
+    if (h_targets->point_base < 0 || h_targets->frame_base < 0 || h_targets->capacity < 0 || h_targets->frame_capacity < 0) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_gather: negative base");
     ctx->gather.n = h_targets->n_targets;
     for (int k = 0; k < h_targets->n_targets; ++k) {
         ctx->gather.xyz[k] = h_targets->xyz[k]; ctx->gather.label[k] = h_targets->label[k]; ctx->gather.frame_offset[k] = h_targets->frame_offset[k];
     }
     ctx->gather.point_base = h_targets->point_base; ctx->gather.frame_base = h_targets->frame_base; ctx->gather.capacity = h_targets->capacity;
+    ctx->gather.frame_capacity = h_targets->frame_capacity;
     return LRC_OK;
 }

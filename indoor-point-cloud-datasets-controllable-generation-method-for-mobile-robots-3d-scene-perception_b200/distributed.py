@@ -285,6 +285,7 @@ class PeerGather:
         g.point_base = self.rank * self.cap
         g.frame_base = self.rank * (self.pmax + 1)
         g.capacity = self.cap
+        g.frame_capacity = self.pmax + 1      # a scan of more frames than this rank's offset region holds is refused
         self._g = g
         self.buffer = torch.as_tensor(_RawCudaBuffer(self.local_ptr, self.nbytes), device=ctx.device)
         if w > 1:
@@ -312,19 +313,60 @@ class PeerGather:
         off = self.buffer[self.o_off: self.o_off + w * (self.pmax + 1) * 8].view(torch.int64).view(w, self.pmax + 1)
         return xyz, lab, off
 
-    def assemble_numpy(self, frames_per_rank: Optional[List[int]] = None) -> Dict[str, np.ndarray]:
-        """Dense, pose-ordered cloud of all ranks (testing / export)."""
+    def incident(self, poses_all, frames_per_rank: Optional[List[int]] = None) -> torch.Tensor:
+        """Incident angles of the WHOLE gathered cloud, recomputed on arrival: (world, cap) float64, row r holds the
+        angles of rank r's points (valid up to that rank's point count).
+
+        The reference's frame is ``(points, incident_angles)`` (raycast_engine_cpu.py:111); the angle is a pure function
+        of the float32 point and the frame's sensor position (:95-107), so the exchange moves 16 B per point (xyz + label)
+        and ``lrc_incident_angles`` redoes the float64 arithmetic here with the operations of the scan's own epilogue --
+        the result is bit-identical to the angles the producing rank computed (``tests/test_gpu_multi.py``).
+        ``poses_all``: the (P_total,4,4) poses in rank order, rank r owning ``frames_per_rank[r]`` of them (default:
+        ``frames_per_rank`` of the constructor for every rank).  Call after ``synchronize()``."""
+        import ctypes as C
+        from . import _native as nat
+        w = self.world
+        nfs = [self.pmax] * w if frames_per_rank is None else [int(x) for x in frames_per_rank]
+        poses = np.ascontiguousarray(poses_all, dtype=np.float64).reshape(-1, 16)
+        if len(poses) != sum(nfs):
+            raise ValueError("poses_all must hold one pose per gathered frame")
+        ctx = self.ctx
+        with torch.cuda.device(ctx.device):
+            poses_d = torch.from_numpy(poses).to(ctx.device)
+            if getattr(self, "_incident", None) is None:
+                self._incident = torch.zeros((w, self.cap), dtype=torch.float64, device=ctx.device)
+            xyz, _, off = self.views()
+            p0 = 0
+            for r in range(w):
+                if nfs[r] > 0:
+                    nat.check(ctx._h, ctx._lib.lrc_incident_angles(
+                        ctx._h, C.c_void_p(xyz[r].data_ptr()), C.c_void_p(off[r].data_ptr()), nfs[r],
+                        C.c_void_p(poses_d[p0:p0 + nfs[r]].data_ptr()), self.cap, C.c_void_p(self._incident[r].data_ptr()),
+                        ctx._stream()))
+                p0 += nfs[r]
+            torch.cuda.current_stream(ctx.device).synchronize()       # poses_d may be freed after return
+        return self._incident
+
+    def assemble_numpy(self, frames_per_rank: Optional[List[int]] = None, poses_all=None) -> Dict[str, np.ndarray]:
+        """Dense, pose-ordered cloud of all ranks (testing / export).  With ``poses_all`` the record is the reference's
+        complete frame: ``incident`` is recomputed from (point, pose) on this rank (see ``incident``)."""
         xyz, lab, off = self.views()
-        pts, labs, counts = [], [], []
+        inc = None if poses_all is None else self.incident(poses_all, frames_per_rank)
+        pts, labs, counts, incs = [], [], [], []
         for r in range(self.world):
             nf = self.pmax if frames_per_rank is None else frames_per_rank[r]
             o = off[r, : nf + 1].cpu().numpy() - r * self.cap
             m = int(o[-1])
             pts.append(xyz[r, :m].cpu().numpy()); labs.append(lab[r, :m].cpu().numpy().view(np.uint32))
+            if inc is not None:
+                incs.append(inc[r, :m].cpu().numpy())
             counts.append(np.diff(o))
         cnt = np.concatenate(counts)
-        return {"points": np.concatenate(pts), "label": np.concatenate(labs),
-                "frame_offset": np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)}
+        out = {"points": np.concatenate(pts), "label": np.concatenate(labs),
+               "frame_offset": np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)}
+        if inc is not None:
+            out["incident"] = np.concatenate(incs)
+        return out
 
     def close(self):
         lib = self.ctx._lib

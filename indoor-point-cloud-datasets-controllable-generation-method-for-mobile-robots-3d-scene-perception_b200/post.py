@@ -159,10 +159,11 @@ class LabelTransfer:
         self.ctx = ctx
         pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
         self.n = len(pts)
+        self._cell = float(cell)
         dev = ctx.device
         with torch.cuda.device(dev):
             self._pts = torch.from_numpy(pts).to(dev)
-            nat.check(ctx._h, ctx._lib.lrc_nn_index_build(ctx._h, _ptr(self._pts), self.n, float(cell), ctx._stream()))
+            self._build_index()
         self._lab = self._rgb = None
         if semantic is not None or instance is not None:
             sem = np.zeros(self.n, np.uint32) if semantic is None else np.asarray(semantic).astype(np.uint32)
@@ -175,11 +176,21 @@ class LabelTransfer:
                 c = (c * 255).astype(np.uint8)                   # reference :483
             self._rgb = torch.from_numpy(pack_rgb(c).view(np.int32)).to(dev)
 
+    def _build_index(self) -> None:
+        ctx = self.ctx
+        nat.check(ctx._h, ctx._lib.lrc_nn_index_build(ctx._h, _ptr(self._pts), self.n, self._cell, ctx._stream()))
+        # the context holds ONE nearest-neighbour index; the label / colour tables live here.  Remember which build is
+        # ours: if another LabelTransfer (another room) has re-targeted the slot, query() re-bins OUR points first --
+        # the reference fits a fresh tree per call (s3dis_sim_scene.py:413-424), so objects never share state there.
+        self._generation = ctx.stat("nn_generation")
+
     def query(self, points, want_distance: bool = False) -> Dict[str, torch.Tensor]:
         """points: (M,3) float32 (device tensor or ndarray).  -> device tensors: index int32, label / rgb int32 holding
         uint32 bits (present when the tables were given), distance float64 (optional)."""
         ctx = self.ctx
         with torch.cuda.device(ctx.device):
+            if ctx.stat("nn_generation") != self._generation:
+                self._build_index()
             q = points if isinstance(points, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(points, dtype=np.float32))
             q = q.to(device=ctx.device, dtype=torch.float32).contiguous().reshape(-1, 3)
             M = q.shape[0]

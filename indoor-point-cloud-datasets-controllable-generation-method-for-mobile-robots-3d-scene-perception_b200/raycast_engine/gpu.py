@@ -80,7 +80,16 @@ class RaycastEngineGPU(RaycastEngineBase):
             print(f"[RaycastEngineGPU] LBVH built: {self.ctx.bvh_info()}")
 
     def set_mesh(self, mesh) -> None:
-        self._prepare(mesh)
+        """Build the BVH of ``mesh`` now and pin the object: per-waypoint calls that pass this same object skip the
+        content check (a CRC over all vertices, indices and labels, ~6 ms per million triangles) that otherwise guards
+        the BVH cache.  Do not edit the mesh arrays in place while it is pinned; ``invalidate_mesh()`` un-pins."""
+        built = self.ctx.pin_mesh(mesh)
+        if built and self.verbose:
+            print(f"[RaycastEngineGPU] LBVH built: {self.ctx.bvh_info()}")
+
+    def invalidate_mesh(self) -> None:
+        """Forget the pinned mesh and the cached fingerprint: the next call rebuilds the BVH."""
+        self.ctx.invalidate_mesh()
 
     def cast_rays(self, rays: np.ndarray, mesh=None):
         """Dense closest-hit query: (t_hit float32 [N] (+inf = miss), primitive_ids uint32 [N] (0xFFFFFFFF = miss))

@@ -92,8 +92,15 @@ class AutoTrajectoryGenerator:
         ctx = self.ctx
         with torch.cuda.device(ctx.device):
             self._verts_d = torch.from_numpy(v).to(ctx.device)
-            nat.check(ctx._h, ctx._lib.lrc_collision_index_build(ctx._h, C.c_void_p(self._verts_d.data_ptr()), v.shape[0],
-                                                                 max(2.0 * self.robot_radius, 1e-3), ctx._stream()))
+            self._build_index()
+
+    def _build_index(self) -> None:
+        ctx = self.ctx
+        nat.check(ctx._h, ctx._lib.lrc_collision_index_build(ctx._h, C.c_void_p(self._verts_d.data_ptr()), self._verts_d.shape[0],
+                                                             max(2.0 * self.robot_radius, 1e-3), ctx._stream()))
+        # the context holds ONE collision index: remember which build is ours, so a query after somebody else's build
+        # (another planner on the same GPU) re-bins our vertices instead of silently testing theirs
+        self._index_generation = ctx.stat("collision_generation")
 
     def _query(self, points: np.ndarray, bounds: Optional[Dict[str, float]]) -> np.ndarray:
         """state per point: 0 = robot cube leaves the room, 1 = a vertex inside the cube, 2 = free."""
@@ -102,6 +109,10 @@ class AutoTrajectoryGenerator:
             return np.zeros(0, np.uint8)
         ctx = self.ctx
         with torch.cuda.device(ctx.device):
+            if getattr(self, "_verts_d", None) is None:
+                raise RuntimeError("no mesh indexed yet: call _index_mesh / generate_optimal_trajectory first")
+            if ctx.stat("collision_generation") != self._index_generation:
+                self._build_index()
             p_d = torch.from_numpy(pts).to(ctx.device)
             st = torch.empty(len(pts), dtype=torch.uint8, device=ctx.device)
             b = None if bounds is None else (C.c_double * 6)(*[float(bounds[k]) for k in _B_KEYS])

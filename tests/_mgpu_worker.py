@@ -56,10 +56,18 @@ def main():
         for _ in range(2):
             local = engine.simulate(poses12[sl.start:sl.stop], intr, noise=local_noise).numpy()
         pg.synchronize()
-        got = pg.assemble_numpy()
+        got = pg.assemble_numpy(poses_all=poses12)
         assert np.array_equal(got["frame_offset"], ref["frame_offset"]), ramp
         assert np.array_equal(got["points"], ref["points"]) and np.array_equal(got["label"], ref["label"]), ramp
+        # the reference's frame is (points, incident angles): the angles are recomputed on arrival, bit for bit
+        assert np.array_equal(got["incident"], ref["incident"]), ramp
         dist.barrier()
+    # a scan of more frames than this rank's offset region holds must be refused, not spill into the neighbour's region
+    try:
+        engine.simulate(poses12[:7], intr, noise=local_noise)
+        raise AssertionError("expected LRC_ERR_CAPACITY")
+    except RuntimeError as e:
+        assert "frame_capacity" in str(e), e
     pg.disable()
     engine.ctx.set_option("gather_ramp", 1)
     a, b = ref["frame_offset"][sl.start], ref["frame_offset"][sl.stop]

@@ -345,21 +345,21 @@ def test_all_traversal_variants_and_block_sizes_give_identical_bits(engine, lrc,
                 for k in ref:
                     assert np.array_equal(got[k], ref[k]), (var, blk, top, k)
             # 32-byte quantised node records: a different tree encoding, the same bits out
-            ctx.set_option("node_format", 1); ctx._mesh_key = None
+            ctx.set_option("node_format", 1); ctx.invalidate_mesh()
             try:
                 got = engine.simulate(poses, intr, mesh).numpy()
                 assert engine.ctx.bvh_info()["bytes_nodes"] == 32 * engine.ctx.bvh_info()["num_nodes"]
             finally:
-                ctx.set_option("node_format", 0); ctx._mesh_key = None
+                ctx.set_option("node_format", 0); ctx.invalidate_mesh()
             for k in ref:
                 assert np.array_equal(got[k], ref[k]), ("node_format 1", k)
             # multi-triangle leaves (2, 4, 8 Morton-consecutive triangles per leaf), under both record formats
             for leaf, fmt in ((1, 0), (4, 0), (8, 0), (1, 1), (4, 1)):
-                ctx.set_option("leaf_size", leaf); ctx.set_option("node_format", fmt); ctx._mesh_key = None
+                ctx.set_option("leaf_size", leaf); ctx.set_option("node_format", fmt); ctx.invalidate_mesh()
                 try:
                     got = engine.simulate(poses, intr, mesh).numpy()
                 finally:
-                    ctx.set_option("leaf_size", 2); ctx.set_option("node_format", 0); ctx._mesh_key = None
+                    ctx.set_option("leaf_size", 2); ctx.set_option("node_format", 0); ctx.invalidate_mesh()
                 for k in ref:
                     assert np.array_equal(got[k], ref[k]), ("leaf_size", leaf, fmt, k)
     finally:

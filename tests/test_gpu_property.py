@@ -24,7 +24,7 @@ def test_random_soups_bvh_equals_exhaustive(engine, lrc, orc, seed, n_tri, n_ray
     engine.ctx.set_option("persistent", persistent)            # one block per 128 rays / persistent warps over 32-ray tiles
     engine.ctx.set_option("compact_nodes", int(compact))        # dead node records kept / squeezed out: identical results
     engine.ctx.set_option("rays_per_thread", rpt)              # 1 / 2 / 4 adjacent rays per thread (format 2 only): identical results
-    engine.ctx._mesh_key = None
+    engine.ctx.invalidate_mesh()
     rng = np.random.default_rng(seed)
     centre = rng.standard_normal((n_tri, 1, 3)) * scale
     verts = (centre + rng.standard_normal((n_tri, 3, 3)) * scale * rng.choice([0.01, 0.3])).reshape(-1, 3)
@@ -61,4 +61,4 @@ def test_random_soups_bvh_equals_exhaustive(engine, lrc, orc, seed, n_tri, n_ray
     engine.ctx.set_option("variant", 65)
     engine.ctx.set_option("persistent", 0)
     engine.ctx.set_option("rays_per_thread", 1)
-    engine.ctx._mesh_key = None
+    engine.ctx.invalidate_mesh()
