@@ -210,8 +210,7 @@ def test_dual_axis_trajectory_with_noise_and_labels(engine, lrc, orc, c1):
         t, pid = scene.cast_rays(rays)
         fr = orc.epilogue_c(rays, t, pid, center=poses[p][:3, 3], max_range=intr.max_range, tri_label=labels, keep=keep.astype(np.uint8))
         a, b = out["frame_offset"][p], out["frame_offset"][p + 1]
-        # the device's float64 sin/cos may round a direction differently in the last float32 bit; such rays can
-        # (rarely) land on a neighbouring triangle.  Compare ray by ray via ray_idx.
+        # compare ray by ray via ray_idx; the id budget is the north-star's grazing-edge tie rate (1e-5 of rays)
         assert np.array_equal(out["ray_idx"][a:b], fr.ray_idx)          # same rays survive dropout / hit / range
         same = out["prim_id"][a:b] == fr.prim_id
         total += len(same)
@@ -219,7 +218,7 @@ def test_dual_axis_trajectory_with_noise_and_labels(engine, lrc, orc, c1):
         assert np.abs(out["points"][a:b][same] - fr.points[same]).max() <= T_TOL
         assert np.array_equal(out["label"][a:b], labels[out["prim_id"][a:b]])
         assert abs(keep.mean() - 0.98) < 0.004
-    assert bad / total <= 1e-4
+    assert bad / total <= 1e-5, (bad, total)
 
 
 # ---- edge cases -----------------------------------------------------------------------------------
