@@ -47,19 +47,42 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu into csrc/liblrc.so for sm_100a.  Returns the library path."""
     if not force and not _stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    env = dict(os.environ)
+    nvcc = [_nvcc()]
     # the image exports CC=/opt/gcc/bin/gcc, which lacks some specs; nvcc must use the system g++
     if os.path.exists("/usr/bin/g++"):
-        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
-    res = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        nvcc += ["-ccbin", "/usr/bin/g++"]
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+    hdr_time = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS)
+    hdr_time = max(hdr_time, os.path.getmtime(os.path.abspath(__file__)))
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        path = os.path.join(CSRC, src)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(path), hdr_time):
+            return src, 0, "(up to date)\n"
+        cmd = nvcc + NVCC_FLAGS + ["-c", "-o", obj, path]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        return src, r.returncode, " ".join(cmd) + "\n" + r.stdout
+
+    # one translation unit per source, compiled side by side (scan.cu with its kernel variants dominates), then linked
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    text = "".join(out for _, _, out in results)
+    rc = max(code for _, code, _ in results)
+    if rc == 0:
+        cmd = nvcc + ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + [os.path.join(objdir, s.replace(".cu", ".o")) for s in SOURCES]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        text += " ".join(cmd) + "\n" + r.stdout
+        rc = r.returncode
     log = os.path.join(CSRC, "build.log")
     with open(log, "w") as f:
-        f.write(" ".join(cmd) + "\n" + res.stdout)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout)
-    if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed ({res.returncode}); see {log}")
+        f.write(text)
+    if verbose or rc != 0:
+        sys.stderr.write(text)
+    if rc != 0:
+        raise RuntimeError(f"nvcc failed ({rc}); see {log}")
     return LIB
 
 

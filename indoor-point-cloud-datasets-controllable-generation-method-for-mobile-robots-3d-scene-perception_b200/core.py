@@ -487,6 +487,34 @@ class Context:
                 res[k] = host[k][:m].numpy().view(np.uint32)
         return res
 
+    def scan_frame_to_host(self, pose, intr, noise: Optional[NoiseConfig] = None):
+        """ONE frame, host in / host out, one library call and one synchronisation: the reference's per-waypoint call
+        pattern (s3dis_simulator.py:254-263).  The pose goes up from host memory, points and incident angles come back
+        through page-locked staging kept by this context (``lrc_scan_*_host`` copies a small frame at capacity right
+        behind its kernels instead of waiting for the point count first) and are returned as fresh numpy arrays.
+        -> (points (m,3) float32, incident (m,) float64)"""
+        dual = is_dual_axis(intr)
+        d = dual_axis_desc(intr) if dual else single_axis_desc(intr)
+        n = d.num_lines * d.points_per_line if dual else d.H * d.W
+        st = getattr(self, "_frame_host", None)
+        if st is None or st[0].shape[0] < n:
+            cap = max(n, 1)
+            st = (torch.empty((cap, 3), dtype=torch.float32).pin_memory(), torch.empty(cap, dtype=torch.float64).pin_memory(),
+                  torch.zeros(2, dtype=torch.int64).pin_memory())
+            self._frame_host = st
+        pose_h = np.ascontiguousarray(pose, dtype=np.float64).reshape(16)
+        out = nat.Out(C.c_void_p(st[0].data_ptr()), C.c_void_p(st[1].data_ptr()), None, None, None, C.c_void_p(st[2].data_ptr()), int(st[0].shape[0]))
+        nz = noise.struct() if noise is not None else None
+        total = C.c_int64(0)
+        fn = self._lib.lrc_scan_dual_axis_host if dual else self._lib.lrc_scan_single_axis_host
+        with torch.cuda.device(self.device):
+            nat.check(self._h, fn(self._h, C.c_void_p(pose_h.ctypes.data), 1, C.byref(d), C.byref(nz) if nz is not None else None,
+                                  C.byref(out), 1, C.byref(total)))
+        m = int(total.value)
+        if m == 0:
+            return np.zeros((0, 3), np.float32), np.empty(0)
+        return st[0][:m].numpy().copy(), st[1][:m].numpy().copy()
+
     def set_mesh_host(self, verts: np.ndarray, tris: np.ndarray, labels: Optional[np.ndarray] = None) -> None:
         """``lrc_set_mesh_host``: upload float32 vertices / int32 indices / uint32 labels from host memory (pinned
         tensors or numpy arrays) and build the LBVH.  Synchronous."""

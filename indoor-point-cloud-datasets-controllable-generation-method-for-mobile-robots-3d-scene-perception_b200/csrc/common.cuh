@@ -60,11 +60,13 @@ struct lrc_ctx {
     // ---- grow-only scratch ----
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    cudaEvent_t tables_event = nullptr;    // recorded after the ray tables were (re)built
     cudaEvent_t scratch_event = nullptr;   // recorded after the last scan that used the scratch
     void* scratch2 = nullptr;     // scan bookkeeping (tile status words, ticket, running total)
     size_t scratch2_bytes = 0;
     double* tables = nullptr;     // ray-generation tables
     size_t tables_bytes = 0;
+    std::vector<double> tables_key;   // the sensor the resident tables were built for: W, H, mode, fov_up, fov_down, elevations
 
     // ---- host-buffer entry points (lrc_*_host): internal streams, staging, device outputs ----
     cudaStream_t s_compute = nullptr, s_copy = nullptr, s_count = nullptr;
@@ -129,6 +131,8 @@ struct lrc_ctx {
 
     // ---- options ----
     int64_t opt_rays_per_thread = 1;    // scan kernels: adjacent rays per thread (1, 2, 4); > 1 needs node format 2
+    int64_t opt_warp_packet = 0;        // scan kernels, format 2: the warp walks the tree together (k_trace_w)
+    int64_t opt_tune = 0;               // format-2 kernel: bit 0 prefetch pushed records, bit 1 no block barrier, bit 2 streaming scratch stores
     int64_t opt_persistent = 0;         // 1: persistent warps over 32-ray tiles (VARIANT bit 8) instead of one block per 128 rays
     int num_sms = 148;
     int64_t opt_block = 128;            // threads per traversal block

@@ -167,7 +167,7 @@ struct FrameMath {
 };
 
 // One ray's share of the frame arithmetic (see above): writes the scratch record of ray idx, returns whether it is kept.
-template <int MODE>
+template <int MODE, bool CS = false>
 __device__ __forceinline__ bool frame_epilogue(const RayGen& g, const FrameMath& fm, int64_t idx, int64_t pose, int r, float ox, float oy,
                                                float oz, float dx, float dy, float dz, float t, uint32_t id, float4* __restrict__ hp,
                                                double* __restrict__ inc_out)
@@ -195,8 +195,13 @@ __device__ __forceinline__ bool frame_epilogue(const RayGen& g, const FrameMath&
         }
         if (keep) o.w = __uint_as_float(id);
     }
-    hp[idx] = o;
-    if (inc_out) inc_out[idx] = inc;
+    if (CS) {      // evict-first: the scratch is read once by k_compact and should not push BVH lines out of L2
+        __stcs(hp + idx, o);
+        if (inc_out) __stcs(inc_out + idx, inc);
+    } else {
+        hp[idx] = o;
+        if (inc_out) inc_out[idx] = inc;
+    }
     return keep;
 }
 
@@ -227,7 +232,7 @@ __device__ __forceinline__ bool trace_one(const RayGen& g, const FrameMath& fm, 
         prim_id[idx] = id;
         return false;
     }
-    return frame_epilogue<MODE>(g, fm, idx, pose, r, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, t, id, hp, inc_out);
+    return frame_epilogue<MODE, (VARIANT & 4096) != 0>(g, fm, idx, pose, r, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, t, id, hp, inc_out);
 }
 
 // VARIANT bit 8 ("persistent"): the grid is sized to fill the machine once and every WARP keeps fetching work -- one
@@ -244,6 +249,12 @@ k_trace(RayGen g, FrameMath fm, const float4* __restrict__ nodes, const float4* 
 {
     extern __shared__ float4 s_top[];
     constexpr bool PERSIST = (VARIANT & 256) != 0;
+    constexpr bool NOBAR = (VARIANT & 2048) != 0 && !PERSIST && !OUT_DENSE;
+    __shared__ unsigned s_keep, s_done;
+    if (NOBAR) {          // all warps of the block are still together here: this barrier costs nothing
+        if (threadIdx.x == 0) { s_keep = 0u; s_done = 0u; }
+        __syncthreads();
+    }
     if (VARIANT & 8) {      // stage the top of the tree (heap order, built by lrc_set_mesh) in shared memory
         for (int i = threadIdx.x; i < 4 * top_n; i += blockDim.x) s_top[i] = __ldg(top_table + i);
         __syncthreads();
@@ -271,7 +282,19 @@ k_trace(RayGen g, FrameMath fm, const float4* __restrict__ nodes, const float4* 
         const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         bool keep = false;
         if (idx < n) keep = trace_one<MODE, COUNT, OUT_DENSE, VARIANT>(g, fm, nodes, tris, idx, has_tris, hp, inc_out, t_hit, prim_id, s_top, top_n, stack_levels, nq, root, nn, nt, nr, nh);
-        if (!OUT_DENSE) {
+        if (NOBAR) {
+            // per-warp keep counts meet in shared memory; the warp that arrives last publishes the block's count.  No warp
+            // waits for the block's slowest ray: its slot is free for the next block's warps as soon as it is done.
+            const unsigned c = __popc(__ballot_sync(0xffffffffu, keep));
+            if (lane_id() == 0) {
+                atomicAdd(&s_keep, c);
+                __threadfence_block();
+                if (atomicAdd(&s_done, 1u) == (blockDim.x >> 5) - 1u) {
+                    __threadfence_block();
+                    block_count[blockIdx.x] = atomicAdd(&s_keep, 0u);
+                }
+            }
+        } else if (!OUT_DENSE) {
             const int c = __syncthreads_count(keep ? 1 : 0);
             if (threadIdx.x == 0) block_count[blockIdx.x] = (unsigned)c;
         }
@@ -336,6 +359,49 @@ k_trace_k(RayGen g, FrameMath fm, const float4* __restrict__ nodes, const float4
     if (lane_id() == 0 && wsum) atomicAdd(&s_cnt[(threadIdx.x * K) / TRACE_THREADS], wsum);
     __syncthreads();
     if (threadIdx.x < K && ((int64_t)blockIdx.x * K + threadIdx.x) * TRACE_THREADS < n) block_count[(int64_t)blockIdx.x * K + threadIdx.x] = s_cnt[threadIdx.x];
+    if (COUNT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            nn += __shfl_xor_sync(0xffffffffu, nn, o);
+            nt += __shfl_xor_sync(0xffffffffu, nt, o);
+            nr += __shfl_xor_sync(0xffffffffu, nr, o);
+            nh += __shfl_xor_sync(0xffffffffu, nh, o);
+        }
+        if (lane_id() == 0) {
+            atomicAdd(&counters[0], (unsigned long long)nr);
+            atomicAdd(&counters[1], (unsigned long long)nn);
+            atomicAdd(&counters[2], (unsigned long long)nt);
+            atomicAdd(&counters[3], (unsigned long long)nh);
+        }
+    }
+}
+
+// Warp packets (traverse.cuh trace_warp): one ray per thread as in k_trace, but the warp walks the tree together with
+// one shared-memory stack per warp.  Scan modes only -- explicit rays carry no promise of coherence.
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(TRACE_THREADS, 12)
+k_trace_w(RayGen g, FrameMath fm, const float4* __restrict__ nodes, const float4* __restrict__ tris, int64_t n, int has_tris,
+          float4* __restrict__ hp, double* __restrict__ inc_out, unsigned* __restrict__ block_count, unsigned long long* counters, int root)
+{
+    __shared__ int s_link[TRACE_THREADS / 32][LRC_WSTACK];
+    __shared__ unsigned s_t[TRACE_THREADS / 32][LRC_WSTACK];
+    const int w = threadIdx.x >> 5;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned nn = 0, nt = 0, nr = 0, nh = 0;
+    int64_t pose = 0; int r = 0;
+    Ray ray;
+    ray.ox = ray.oy = ray.oz = 0.f; ray.dx = 1.f; ray.dy = ray.dz = 0.f; ray.keep = false;
+    if (idx < n) ray = gen_ray<MODE>(g, idx, pose, r);
+    const bool live = idx < n && ray.keep && has_tris;
+    float t; uint32_t id;
+    trace_warp<COUNT>(nodes, tris, root, s_link[w], s_t[w], ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, live, t, id, nn, nt);
+    if (!live) { t = LRC_INF; id = LRC_MISS_ID; }
+    nr += live;
+    nh += id != LRC_MISS_ID;
+    bool keep = false;
+    if (idx < n) keep = frame_epilogue<MODE>(g, fm, idx, pose, r, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, t, id, hp, inc_out);
+    const int c = __syncthreads_count(keep ? 1 : 0);
+    if (threadIdx.x == 0) block_count[blockIdx.x] = (unsigned)c;
     if (COUNT) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -587,6 +653,7 @@ int ensure_counters(lrc_ctx* ctx)
 
 // rays per thread of the scan kernels: > 1 needs the paired node records (format 2) and 128-ray compaction blocks
 inline int packet_rays(const lrc_ctx* ctx) { return ctx->node_format == 2 ? (int)ctx->opt_rays_per_thread : 1; }
+inline bool warp_packets(const lrc_ctx* ctx) { return ctx->opt_warp_packet && ctx->node_format == 2 && ctx->opt_block == TRACE_THREADS && packet_rays(ctx) == 1; }
 inline int scan_block_threads(const lrc_ctx* ctx) { return packet_rays(ctx) > 1 ? TRACE_THREADS : (int)ctx->opt_block; }
 
 template <int MODE, bool DENSE>
@@ -605,6 +672,13 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
         else { if (K == 2) LRC_LAUNCH_PACKET(false, 2); else LRC_LAUNCH_PACKET(false, 4); }
 #undef LRC_LAUNCH_PACKET
         LRC_CHECK_LAUNCH(ctx, "k_trace_k");
+        return LRC_OK;
+    }
+    if (!DENSE && MODE != MODE_RAYS && warp_packets(ctx)) {
+        const unsigned wgrid = (unsigned)((n + TRACE_THREADS - 1) / TRACE_THREADS);
+        if (ctx->counting) k_trace_w<MODE, true><<<wgrid, TRACE_THREADS, 0, stream>>>(g, fm, ctx->nodes, ctx->tris, n, has_tris, hp, inc, block_count, ctx->d_counters, ctx->root);
+        else k_trace_w<MODE, false><<<wgrid, TRACE_THREADS, 0, stream>>>(g, fm, ctx->nodes, ctx->tris, n, has_tris, hp, inc, block_count, ctx->d_counters, ctx->root);
+        LRC_CHECK_LAUNCH(ctx, "k_trace_w");
         return LRC_OK;
     }
     const int TB = DENSE ? TRACE_THREADS : (int)ctx->opt_block;
@@ -633,6 +707,7 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
     const int root = ctx->root;
     // the resident tree's record format selects the kernel family; the variant option tunes the float-format kernels
     int64_t variant = ctx->node_format == 1 ? 37 : ctx->node_format == 2 ? ((ctx->opt_variant & 64) ? 193 : 129) : ctx->opt_variant;
+    if (variant == 193 && ctx->opt_tune) variant |= (ctx->opt_tune & 7) << 10;     // bits 10..12: prefetch, no barrier, streaming stores
     int tile_shift = 0;
     if (ctx->opt_persistent && (variant == 1 || variant == 65 || variant == 129 || variant == 193)) {
         variant |= 256;
@@ -667,6 +742,11 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
             case 385: LRC_LAUNCH_TRACE(true, 385); break;
             case 449: LRC_LAUNCH_TRACE(true, 449); break;
             case 961: LRC_LAUNCH_TRACE(true, 961); break;
+            case 1217: LRC_LAUNCH_TRACE(true, 1217); break;
+            case 2241: LRC_LAUNCH_TRACE(true, 2241); break;
+            case 4289: LRC_LAUNCH_TRACE(true, 4289); break;
+            case 6337: LRC_LAUNCH_TRACE(true, 6337); break;
+            case 7361: LRC_LAUNCH_TRACE(true, 7361); break;
             default: LRC_LAUNCH_TRACE(true, 3); break;
         }
     } else {
@@ -686,6 +766,11 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
             case 385: LRC_LAUNCH_TRACE(false, 385); break;
             case 449: LRC_LAUNCH_TRACE(false, 449); break;
             case 961: LRC_LAUNCH_TRACE(false, 961); break;
+            case 1217: LRC_LAUNCH_TRACE(false, 1217); break;
+            case 2241: LRC_LAUNCH_TRACE(false, 2241); break;
+            case 4289: LRC_LAUNCH_TRACE(false, 4289); break;
+            case 6337: LRC_LAUNCH_TRACE(false, 6337); break;
+            case 7361: LRC_LAUNCH_TRACE(false, 7361); break;
             default: LRC_LAUNCH_TRACE(false, 3); break;
         }
     }
@@ -859,16 +944,33 @@ int fill_single(lrc_ctx* ctx, const lrc_single_axis* s, const double* poses, Ray
     g.H = s->H; g.W = s->W; g.N = s->H * s->W;
     g.uniform_mode = s->h_vertical_deg ? 0 : 1;
     const size_t n_tab = (size_t)2 * s->W + 2 * s->H;
-    int rc = lrc_grow(ctx, (void**)&ctx->tables, &ctx->tables_bytes, sizeof(double) * (n_tab + s->H));
-    if (rc) return rc;
-    double* vdeg = ctx->tables + n_tab;
-    // the tables are shared by every scan of this context: a scan still running on another stream must finish with them first
-    if (ctx->scratch_event) LRC_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->scratch_event, 0));
-    if (s->h_vertical_deg)
-        LRC_CUDA(ctx, cudaMemcpyAsync(vdeg, s->h_vertical_deg, sizeof(double) * s->H, cudaMemcpyHostToDevice, stream));
-    const int n = s->W + s->H;
-    k_single_tables<<<(n + 255) / 256, 256, 0, stream>>>(ctx->tables, s->W, s->H, vdeg, g.uniform_mode, s->fov_up_deg, s->fov_down_deg);
-    LRC_CHECK_LAUNCH(ctx, "k_single_tables");
+    // the per-waypoint call pattern presents the same sensor thousands of times: keep the tables while the sensor is unchanged
+    std::vector<double> key;
+    key.reserve(5 + (size_t)(s->h_vertical_deg ? s->H : 0));
+    key.push_back((double)s->W); key.push_back((double)s->H); key.push_back((double)g.uniform_mode);
+    key.push_back(s->fov_up_deg); key.push_back(s->fov_down_deg);
+    if (s->h_vertical_deg) key.insert(key.end(), s->h_vertical_deg, s->h_vertical_deg + s->H);
+    const bool same = ctx->tables && key.size() == ctx->tables_key.size() &&
+                      memcmp(key.data(), ctx->tables_key.data(), sizeof(double) * key.size()) == 0;
+    if (!same) {
+        ctx->tables_key.clear();
+        int rc = lrc_grow(ctx, (void**)&ctx->tables, &ctx->tables_bytes, sizeof(double) * (n_tab + s->H));
+        if (rc) return rc;
+        double* vdeg = ctx->tables + n_tab;
+        // the tables are shared by every scan of this context: a scan still running on another stream must finish with them first
+        if (ctx->scratch_event) LRC_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->scratch_event, 0));
+        if (s->h_vertical_deg)
+            LRC_CUDA(ctx, cudaMemcpyAsync(vdeg, s->h_vertical_deg, sizeof(double) * s->H, cudaMemcpyHostToDevice, stream));
+        const int n = s->W + s->H;
+        k_single_tables<<<(n + 255) / 256, 256, 0, stream>>>(ctx->tables, s->W, s->H, vdeg, g.uniform_mode, s->fov_up_deg, s->fov_down_deg);
+        LRC_CHECK_LAUNCH(ctx, "k_single_tables");
+        // later scans may run on other streams: they must see the finished tables
+        if (!ctx->tables_event) LRC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->tables_event, cudaEventDisableTiming));
+        LRC_CUDA(ctx, cudaEventRecord(ctx->tables_event, stream));
+        ctx->tables_key.swap(key);
+    } else if (ctx->tables_event) {
+        LRC_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->tables_event, 0));
+    }
     g.tab = ctx->tables;
     return LRC_OK;
 }
@@ -952,6 +1054,7 @@ extern "C" void lrc_destroy(lrc_ctx* ctx)
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->scratch_event) cudaEventDestroy(ctx->scratch_event);
+    if (ctx->tables_event) cudaEventDestroy(ctx->tables_event);
     for (cudaEvent_t e : ctx->kt_events) cudaEventDestroy(e);
     if (ctx->s_aux) { cudaStreamDestroy(ctx->s_aux); for (int k = 0; k < 4; ++k) cudaEventDestroy(ctx->pipe_ev[k]); }
     for (size_t i = 0; i < ctx->n_events; ++i) cudaEventDestroy(ctx->events[i]);
@@ -1087,6 +1190,12 @@ extern "C" int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value)
     if (!strcmp(key, "persistent")) {
         if (value < 0 || value > 2) return lrc_fail(ctx, LRC_ERR_INVALID, "persistent must be 0, 1 or 2 (2 = 48-register build)");
         ctx->opt_persistent = value;
+        return LRC_OK;
+    }
+    if (!strcmp(key, "warp_packet")) { ctx->opt_warp_packet = value != 0; return LRC_OK; }
+    if (!strcmp(key, "tune")) {
+        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 6 && value != 7) return lrc_fail(ctx, LRC_ERR_INVALID, "tune must be 0, 1, 2, 4, 6 or 7");
+        ctx->opt_tune = value;
         return LRC_OK;
     }
     if (!strcmp(key, "kernel_timing")) { ctx->opt_kernel_timing = value != 0; ctx->kt_used = 0; return LRC_OK; }
@@ -1278,6 +1387,30 @@ int run_scan_host(lrc_ctx* ctx, RayGen g, const double* h_poses, int64_t P, int6
     LRC_CUDA(ctx, cudaMemcpyAsync(d_poses, h_poses, sizeof(double) * 16 * (size_t)P, cudaMemcpyHostToDevice, ctx->s_compute));
     g.poses = d_poses;
     const uint64_t pose_base = g.pose_index_base;
+    // One small frame (the reference's per-waypoint call pattern): a count round trip would double the latency, so the
+    // records are copied at capacity -- at most 6 MB -- right behind the kernels and one synchronisation ends the call.
+    if (n_chunks == 1 && P * N <= ((int64_t)1 << 18)) {
+        lrc_out d;
+        d.xyz = (float*)(base + o_xyz);
+        d.incident_deg = h_out->incident_deg ? (double*)(base + o_inc) : nullptr;
+        d.prim_id = h_out->prim_id ? (uint32_t*)(base + o_prim) : nullptr;
+        d.label = h_out->label ? (uint32_t*)(base + o_lab) : nullptr;
+        d.ray_idx = h_out->ray_idx ? (uint32_t*)(base + o_ray) : nullptr;
+        d.frame_offset = (int64_t*)(base + o_off);
+        d.capacity = P * N;
+        cudaStream_t st = ctx->s_compute;
+        if ((rc = run_scan<MODE>(ctx, g, P, N, nullptr, max_range, &d, st))) return rc;
+        LRC_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage, d.frame_offset, sizeof(int64_t) * (size_t)(P + 1), cudaMemcpyDeviceToHost, st));
+        LRC_CUDA(ctx, cudaMemcpyAsync(h_out->xyz, d.xyz, sizeof(float) * 3 * cap, cudaMemcpyDeviceToHost, st));
+        if (h_out->incident_deg) LRC_CUDA(ctx, cudaMemcpyAsync(h_out->incident_deg, d.incident_deg, sizeof(double) * cap, cudaMemcpyDeviceToHost, st));
+        if (h_out->label) LRC_CUDA(ctx, cudaMemcpyAsync(h_out->label, d.label, sizeof(uint32_t) * cap, cudaMemcpyDeviceToHost, st));
+        if (h_out->prim_id) LRC_CUDA(ctx, cudaMemcpyAsync(h_out->prim_id, d.prim_id, sizeof(uint32_t) * cap, cudaMemcpyDeviceToHost, st));
+        if (h_out->ray_idx) LRC_CUDA(ctx, cudaMemcpyAsync(h_out->ray_idx, d.ray_idx, sizeof(uint32_t) * cap, cudaMemcpyDeviceToHost, st));
+        LRC_CUDA(ctx, cudaStreamSynchronize(st));
+        for (int64_t k = 0; k <= P; ++k) h_out->frame_offset[k] = ctx->h_stage[k];
+        *h_num_points = ctx->h_stage[P];
+        return LRC_OK;
+    }
     // 1) enqueue every chunk's kernels; a tiny copy of each chunk's frame offsets follows on its own stream
     for (size_t c = 0; c < n_chunks; ++c) {
         const int64_t f0 = chunk_start[c];

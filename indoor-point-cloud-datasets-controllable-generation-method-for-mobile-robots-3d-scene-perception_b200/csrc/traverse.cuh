@@ -323,9 +323,16 @@ __device__ __forceinline__ RaySlabP make_slab_p(float ox, float oy, float oz, fl
     return s;
 }
 
-template <bool COUNT, class STACK>
+// bring the record a stack entry points at (node or first triangle of a leaf) towards L1 while the near side is walked
+__device__ __forceinline__ void prefetch_link(const float4* __restrict__ nodes, const float4* __restrict__ tris, int link)
+{
+    const float4* p = link >= 0 ? nodes + 4 * (int64_t)link : tris + 3 * (int64_t)((~(unsigned)link) & 0x0fffffffu);
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+}
+
+template <bool COUNT, class STACK, bool PF = false>
 __device__ __forceinline__ int inner_step_p(const float4* __restrict__ nodes, int cur, const RaySlabP& s, float best_t,
-                                            STACK& stack, int& sp, unsigned& n_nodes)
+                                            STACK& stack, int& sp, unsigned& n_nodes, const float4* __restrict__ tris = nullptr)
 {
     const float4* np = nodes + 4 * (int64_t)cur;
     const float4 A = __ldg(np + 0), B = __ldg(np + 1), Z = __ldg(np + 2);
@@ -344,6 +351,7 @@ __device__ __forceinline__ int inner_step_p(const float4* __restrict__ nodes, in
     const int l0 = __float_as_int(L.x), l1 = __float_as_int(L.y);
     if (h0 && h1) {
         const bool swp = t1 < t0;
+        if (PF) prefetch_link(nodes, tris, swp ? l0 : l1);
         StackOps<STACK>::push(stack, sp, swp ? l0 : l1, swp ? t0 : t1, nullptr, 0);
         return swp ? l1 : l0;
     }
@@ -352,7 +360,7 @@ __device__ __forceinline__ int inner_step_p(const float4* __restrict__ nodes, in
     return StackOps<STACK>::pop(stack, sp, best_t, nullptr, 0);
 }
 
-template <bool COUNT, class STACK>
+template <bool COUNT, class STACK, bool PF = false>
 __device__ __forceinline__ void trace_loop_p(const float4* __restrict__ nodes, const float4* __restrict__ tris, int root, float ox,
                                              float oy, float oz, float dx, float dy, float dz, float& best_t, uint32_t& best_id,
                                              unsigned& n_nodes, unsigned& n_tris)
@@ -364,7 +372,7 @@ __device__ __forceinline__ void trace_loop_p(const float4* __restrict__ nodes, c
     int sp = 0;
     int cur = root;
     while (cur != LRC_SENTINEL) {
-        while (cur >= 0) cur = inner_step_p<COUNT>(nodes, cur, s, best_t, stack, sp, n_nodes);
+        while (cur >= 0) cur = inner_step_p<COUNT, STACK, PF>(nodes, cur, s, best_t, stack, sp, n_nodes, tris);
         if (cur != LRC_SENTINEL) {
             leaf_test(tris, cur, ox, oy, oz, dx, dy, dz, best_t, best_id, n_tris);
             cur = StackOps<STACK>::pop(stack, sp, best_t, nullptr, 0);
@@ -498,6 +506,77 @@ __device__ __forceinline__ void trace_packet(const float4* __restrict__ nodes, c
     }
 }
 
+// ---- warp packets: the 32 rays of a warp walk ONE node at a time (paired node format) -----------------------------------
+// ncu on the one-ray-per-thread kernel: l1tex data-pipe wavefronts 77 % of peak with ~3.3 wavefronts per load instruction --
+// the lanes of a warp sit at ~3 different nodes per step, and every lane keeps its own stack in local memory.  Here `cur`
+// and the stack are WARP-uniform: every record is fetched once per warp at a lane-uniform address (one wavefront per load),
+// the 32 rays are slab-tested against it, a child is entered when ANY lane hits it (ballot), the nearer child -- by the
+// smallest entry distance over the lanes that hit, a REDUX over the float bits, monotone for t >= 0 -- goes first and the
+// other one onto one shared-memory stack per warp, which also carries that smallest entry distance so that a popped entry
+// is dropped when no lane can still improve (largest best hit over the live lanes).  Every lane still culls with its OWN
+// best hit and runs the unchanged Moller-Trumbore test, so the output bits do not change: the warp visits the union of its
+// rays' nodes.  Rays of a warp are 32 adjacent beams of one scan line, which is what keeps that union small.
+#define LRC_WSTACK 64     // entries per warp (tree height is checked against LRC_STACK_DEPTH = 64 at build time)
+
+__device__ __forceinline__ int wstack_pop(const int* s_link, const unsigned* s_t, int& sp, unsigned bmax)
+{
+    while (sp > 0) {
+        --sp;
+        if (s_t[sp] <= bmax) return s_link[sp];
+    }
+    return LRC_SENTINEL;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void trace_warp(const float4* __restrict__ nodes, const float4* __restrict__ tris, int root, int* s_link,
+                                           unsigned* s_t, float ox, float oy, float oz, float dx, float dy, float dz, bool live,
+                                           float& best_t, uint32_t& best_id, unsigned& n_nodes, unsigned& n_tris)
+{
+    const unsigned FULL = 0xffffffffu;
+    best_t = live ? LRC_INF : -1.f;         // a lane without a ray can never enter a box (tfar < 0 <= tnear) nor accept a hit
+    best_id = LRC_MISS_ID;
+    const RaySlabP s = make_slab_p(ox, oy, oz, dx, dy, dz);
+    const float2 naxy = make_float2(-s.axy.x, -s.axy.y), nazz = make_float2(-s.azz.x, -s.azz.y);
+    int sp = 0;
+    unsigned bmax = __reduce_max_sync(FULL, live ? 0x7f800000u : 0u);      // bits of the largest best hit among live lanes
+    int cur = bmax ? root : LRC_SENTINEL;
+    while (cur != LRC_SENTINEL) {
+        while (cur >= 0) {
+            const float4* np = nodes + 4 * (int64_t)cur;
+            const float4 A = __ldg(np + 0), B = __ldg(np + 1), Z = __ldg(np + 2);
+            const float2 L = __ldg(reinterpret_cast<const float2*>(np + 3));
+            if (COUNT) ++n_nodes;
+            const float2 tc0 = ffma2(make_float2(A.x, A.y), s.ixy, s.nxy);
+            const float2 tc1 = ffma2(make_float2(A.z, A.w), s.ixy, s.nxy);
+            const float2 tcz = ffma2(make_float2(Z.x, Z.y), s.izz, s.nzz);
+            const float2 n0 = ffma2(make_float2(B.x, B.y), naxy, tc0), f0 = ffma2(make_float2(B.x, B.y), s.axy, tc0);
+            const float2 n1 = ffma2(make_float2(B.z, B.w), naxy, tc1), f1 = ffma2(make_float2(B.z, B.w), s.axy, tc1);
+            const float2 nz = ffma2(make_float2(Z.z, Z.w), nazz, tcz), fz = ffma2(make_float2(Z.z, Z.w), s.azz, tcz);
+            const float t0 = fmaxf(fmaxf(n0.x, n0.y), fmaxf(nz.x, 0.f)), e0 = fminf(fminf(f0.x, f0.y), fminf(fz.x, best_t));
+            const float t1 = fmaxf(fmaxf(n1.x, n1.y), fmaxf(nz.y, 0.f)), e1 = fminf(fminf(f1.x, f1.y), fminf(fz.y, best_t));
+            const bool h0 = t0 <= e0, h1 = t1 <= e1;
+            const unsigned b0 = __ballot_sync(FULL, h0), b1 = __ballot_sync(FULL, h1);
+            const int l0 = __float_as_int(L.x), l1 = __float_as_int(L.y);
+            if (b0 && b1) {
+                const unsigned m0 = __reduce_min_sync(FULL, h0 ? __float_as_uint(t0) : 0x7f800000u);
+                const unsigned m1 = __reduce_min_sync(FULL, h1 ? __float_as_uint(t1) : 0x7f800000u);
+                const bool swp = m1 < m0;
+                s_link[sp] = swp ? l0 : l1;              // every lane stores the same value to the same word
+                s_t[sp] = swp ? m0 : m1;
+                ++sp;
+                cur = swp ? l1 : l0;
+            } else if (b0) cur = l0;
+            else if (b1) cur = l1;
+            else cur = wstack_pop(s_link, s_t, sp, bmax);
+        }
+        if (cur != LRC_SENTINEL) {
+            leaf_test(tris, cur, ox, oy, oz, dx, dy, dz, best_t, best_id, n_tris);
+            bmax = __reduce_max_sync(FULL, live ? __float_as_uint(best_t) : 0u);
+            cur = wstack_pop(s_link, s_t, sp, bmax);
+        }
+    }
+}
+
 // Stack-based closest-hit traversal.  VARIANT bit 0: 0 = one node (inner or leaf) per loop trip ("if-if"),
 // 1 = "while-while" -- run down inner nodes until a leaf (or the end) is reached, then test the leaf.
 // VARIANT bit 1: node records fetched with 256-bit loads.  VARIANT bit 2 (scan.cu): 32-register cap (64 warps per SM).
@@ -506,6 +585,8 @@ __device__ __forceinline__ void trace_packet(const float4* __restrict__ nodes, c
 // VARIANT bit 5: 32-byte quantised node records (trace_loop_q; while-while only).
 // VARIANT bit 7: paired node records + packed FMA (trace_loop_p, node format 2; with or without bit 6).
 // VARIANT bit 6: stack entries carry their entry distance and are culled against the best hit at pop time (StackCull).
+// VARIANT bit 10: the record of a pushed entry is prefetched towards L1 (paired format).  Bits 11 / 12 live in scan.cu:
+// per-warp keep counts combined through shared-memory atomics instead of a block-wide barrier; streaming scratch stores.
 template <int VARIANT, bool COUNT, class STACK>
 __device__ __forceinline__ void trace_loop(const float4* __restrict__ nodes, const float4* __restrict__ tris,
                                            const float4* s_top, int top_n, int root, STACK& stack, int* sm, int levels, float ox,
@@ -567,7 +648,8 @@ __device__ __forceinline__ void trace_ray(const float4* __restrict__ nodes, cons
                                           uint32_t& best_id, unsigned& n_nodes, unsigned& n_tris)
 {
     if (VARIANT & 128) {
-        if (VARIANT & 64) trace_loop_p<COUNT, StackCull>(nodes, tris, root, ox, oy, oz, dx, dy, dz, best_t, best_id, n_nodes, n_tris);
+        if (VARIANT & 1024) trace_loop_p<COUNT, StackCull, true>(nodes, tris, root, ox, oy, oz, dx, dy, dz, best_t, best_id, n_nodes, n_tris);
+        else if (VARIANT & 64) trace_loop_p<COUNT, StackCull>(nodes, tris, root, ox, oy, oz, dx, dy, dz, best_t, best_id, n_nodes, n_tris);
         else trace_loop_p<COUNT, StackLocal>(nodes, tris, root, ox, oy, oz, dx, dy, dz, best_t, best_id, n_nodes, n_tris);
     } else if (VARIANT & 32) {
         trace_loop_q<COUNT>(nodes, tris, nq, root, ox, oy, oz, dx, dy, dz, best_t, best_id, n_nodes, n_tris);

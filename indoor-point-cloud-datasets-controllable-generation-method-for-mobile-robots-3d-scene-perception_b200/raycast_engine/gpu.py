@@ -32,8 +32,8 @@ class RaycastEngineGPU(RaycastEngineBase):
         self.verbose = verbose
         self.cache_mesh = cache_mesh
         self.ctx: Context = get_context(device)
-        self.last_scan: Optional[ScanResult] = None
-        self._frame_bufs = None
+        self._last_scan: Optional[ScanResult] = None
+        self._last_frame = None           # (pose, intrinsics, noise) of the last per-frame call: ``last_scan`` on demand
 
     # ---- reference interface ------------------------------------------------------------------
     def rays_intersect_mesh(self, rays: np.ndarray, mesh):
@@ -53,14 +53,13 @@ class RaycastEngineGPU(RaycastEngineBase):
         (reference raycast_engine_cpu.py:75-111)."""
         self._prepare(mesh)
         if isinstance(lidar, (IndoorLidar, DualAxisLidar)):
-            # one frame per call is the reference's call pattern: the output buffers are kept per sensor size, so
-            # ``last_scan`` stays valid until the next call
-            from ..core import rays_per_frame
-            n = rays_per_frame(lidar.intrinsics)
-            if self._frame_bufs is None or self._frame_bufs[0] != n:
-                self._frame_bufs = (n, self.ctx._alloc_out(n, 1)[0])
+            # one frame per call is the reference's call pattern (s3dis_simulator.py:254-263): one library call, one
+            # synchronisation, results through the context's page-locked staging.  Triangle ids / labels / ray indices
+            # of the frame are produced only when somebody asks for ``last_scan``.
             noise = lidar.noise_config() if isinstance(lidar, DualAxisLidar) else None
-            res = self.ctx.scan(lidar.pose[None], lidar.intrinsics, noise, bufs=self._frame_bufs[1])
+            pose = np.array(lidar.pose, dtype=np.float64)
+            self._last_scan, self._last_frame = None, (pose, lidar.intrinsics, noise, self.ctx.stat("mesh_generation"))
+            return self.ctx.scan_frame_to_host(pose, lidar.intrinsics, noise)     # empty frame -> np.empty(0), reference :109
         else:
             # duck-typed sensor (the reference touches only get_rays(), pose[:3,3], intrinsics.max_range)
             rays = lidar.get_rays()
@@ -74,6 +73,22 @@ class RaycastEngineGPU(RaycastEngineBase):
         return self.ctx.frame_to_numpy(res)                                          # empty frame -> np.empty(0), reference :109
 
     # ---- extensions ---------------------------------------------------------------------------
+    @property
+    def last_scan(self) -> Optional[ScanResult]:
+        """Device-resident record of the most recent call (points, incident angles, triangle ids, labels, ray indices).
+        After a per-frame ``lidar_intersect_mesh`` it is produced on first access by re-running that frame on the
+        resident BVH (deterministic: same pose, same sensor, same noise counter)."""
+        if self._last_scan is None and self._last_frame is not None:
+            pose, intr, noise, generation = self._last_frame
+            if self.ctx.stat("mesh_generation") != generation:
+                raise RuntimeError("last_scan: the mesh of the last frame is no longer resident (another mesh was set since)")
+            self._last_scan = self.ctx.scan(pose[None], intr, noise)
+        return self._last_scan
+
+    @last_scan.setter
+    def last_scan(self, value) -> None:
+        self._last_scan, self._last_frame = value, None
+
     def _prepare(self, mesh) -> None:
         built = self.ctx.set_mesh(mesh, cache=self.cache_mesh)
         if built and self.verbose:
