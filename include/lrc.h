@@ -285,7 +285,8 @@ int lrc_counters(lrc_ctx* ctx, lrc_counters_t* h_out, int reset, void* stream);
 /* Number of kernel launches issued by this context since creation (for bench.py's gpu_launches). */
 int64_t lrc_launch_count(const lrc_ctx* ctx);
 /* Small integers about the context, by name: "scratch_bytes" (grow-only scan/build scratch currently allocated),
- * "bvh_bytes", "node_format", "build_quality", "ploc_iterations" (of the resident tree), and the generation counters
+ * "bvh_bytes", "node_format", "build_quality", "ploc_iterations" (of the resident tree), the current options "leaf_size",
+ * "variant", "tune", "warp_packet", "rays_per_thread", "persistent", "num_sms", and the generation counters
  * "mesh_generation" / "nn_generation" / "collision_generation", which lrc_set_mesh / lrc_nn_index_build /
  * lrc_collision_index_build bump: the context holds ONE index of each kind, so a host object that built one remembers the
  * generation and rebuilds (or refuses) when somebody else has re-targeted the slot since. */

@@ -132,7 +132,7 @@ struct lrc_ctx {
     // ---- options ----
     int64_t opt_rays_per_thread = 1;    // scan kernels: adjacent rays per thread (1, 2, 4); > 1 needs node format 2
     int64_t opt_warp_packet = 0;        // scan kernels, format 2: the warp walks the tree together (k_trace_w)
-    int64_t opt_tune = 0;               // format-2 kernel: bit 0 prefetch pushed records, bit 1 no block barrier, bit 2 streaming scratch stores
+    int64_t opt_tune = 2;               // format-2 kernel: bit 0 prefetch pushed records, bit 1 no block barrier (default), bit 2 streaming scratch stores
     int64_t opt_persistent = 0;         // 1: persistent warps over 32-ray tiles (VARIANT bit 8) instead of one block per 128 rays
     int num_sms = 148;
     int64_t opt_block = 128;            // threads per traversal block

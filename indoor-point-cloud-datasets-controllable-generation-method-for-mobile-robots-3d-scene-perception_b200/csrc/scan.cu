@@ -1098,6 +1098,13 @@ extern "C" int lrc_get_stat(lrc_ctx* ctx, const char* key, int64_t* h_value)
     if (!strcmp(key, "build_quality")) { *h_value = ctx->build_quality; return LRC_OK; }
     if (!strcmp(key, "ploc_iterations")) { *h_value = ctx->ploc_iterations; return LRC_OK; }
     if (!strcmp(key, "node_format")) { *h_value = ctx->node_format; return LRC_OK; }
+    if (!strcmp(key, "leaf_size")) { *h_value = ctx->opt_leaf_size; return LRC_OK; }
+    if (!strcmp(key, "variant")) { *h_value = ctx->opt_variant; return LRC_OK; }
+    if (!strcmp(key, "tune")) { *h_value = ctx->opt_tune; return LRC_OK; }
+    if (!strcmp(key, "warp_packet")) { *h_value = ctx->opt_warp_packet; return LRC_OK; }
+    if (!strcmp(key, "rays_per_thread")) { *h_value = ctx->opt_rays_per_thread; return LRC_OK; }
+    if (!strcmp(key, "persistent")) { *h_value = ctx->opt_persistent; return LRC_OK; }
+    if (!strcmp(key, "num_sms")) { *h_value = ctx->num_sms; return LRC_OK; }
     if (!strcmp(key, "nn_generation")) { *h_value = ctx->nn_generation; return LRC_OK; }
     if (!strcmp(key, "collision_generation")) { *h_value = ctx->ci_generation; return LRC_OK; }
     if (!strcmp(key, "mesh_generation")) { *h_value = ctx->mesh_generation; return LRC_OK; }

@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """A few device-resident trajectory scans with chosen engine options -- the command profiled under ncu.
 
-    python tools/prof_scan.py --workload c2 --format 2 --variant 65 --rpt 1 --quality 0 --reps 3
+    python tools/prof_scan.py --workload c2 [--format 2 --variant 65 --tune 2 --rpt 1 --quality 0 --wp 0] --reps 3
+
+Options that are not given keep the library's defaults (the build bench.py runs).  Prints the build tag bench.py
+matches a capture against (profiles/traffic.json).
 """
 import argparse
 import os
@@ -19,11 +22,13 @@ import lrc_b200 as lrc  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="c2")
-    ap.add_argument("--format", type=int, default=2)
-    ap.add_argument("--variant", type=int, default=65)
-    ap.add_argument("--rpt", type=int, default=1)
-    ap.add_argument("--quality", type=int, default=0)
-    ap.add_argument("--leaf", type=int, default=2)
+    ap.add_argument("--format", type=int, default=None)
+    ap.add_argument("--variant", type=int, default=None)
+    ap.add_argument("--tune", type=int, default=None)
+    ap.add_argument("--wp", type=int, default=None)
+    ap.add_argument("--rpt", type=int, default=None)
+    ap.add_argument("--quality", type=int, default=None)
+    ap.add_argument("--leaf", type=int, default=None)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--poses", type=int, default=None)
     ap.add_argument("--tris", type=int, default=None)
@@ -31,9 +36,10 @@ def main():
     w, mesh, poses, intr = bench.make_workload(lrc, args.workload, 1, args.tris, args.poses)
     dev = torch.device("cuda", 0)
     ctx = lrc.RaycastEngineGPU(device=0).ctx
-    for k, v in (("node_format", args.format), ("variant", args.variant), ("rays_per_thread", args.rpt), ("build_quality", args.quality),
-                 ("leaf_size", args.leaf)):
-        ctx.set_option(k, v)
+    for k, v in (("node_format", args.format), ("variant", args.variant), ("tune", args.tune), ("warp_packet", args.wp),
+                 ("rays_per_thread", args.rpt), ("build_quality", args.quality), ("leaf_size", args.leaf)):
+        if v is not None:
+            ctx.set_option(k, v)
     v, f, lab = lrc.mesh_arrays(mesh)
     ctx.set_mesh_arrays(v, f, lab)
     noise = lrc.NoiseConfig.from_intrinsics(intr, seed=2) if w["noise"] else None
@@ -46,7 +52,8 @@ def main():
         flush.fill_(r & 255)
         ctx.scan_enqueue(poses_d, intr, noise, bufs)
         torch.cuda.synchronize()
-    print("points", int(bufs["off"][-1].item()))
+    print(json_line := {"workload": args.workload, "tris": int(len(f)), "rays_per_launch": int(P * n_frame), "build_tag": bench.build_tag(ctx),
+                        "points": int(bufs["off"][-1].item())})
 
 
 if __name__ == "__main__":
