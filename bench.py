@@ -301,10 +301,20 @@ def load_capture(workload: str, n_tris: int, rays_per_launch: int, tag: str):
         return None, f"profiles/traffic.json unreadable: {e}"
     if not tj:
         return None, f"no capture for workload {workload}"
-    if int(tj.get("tris", 0)) != int(n_tris) or int(tj.get("rays_per_launch", 0)) != int(rays_per_launch):
-        return None, "capture is of another size"
+    if int(tj.get("tris", 0)) != int(n_tris):
+        return None, "capture is of another mesh size"
     if tj.get("build_tag") != tag:
         return None, f"capture is of another kernel build ({tj.get('build_tag')} vs {tag})"
+    if int(tj.get("rays_per_launch", 0)) != int(rays_per_launch):
+        # same mesh, sensor and kernel, another number of frames per launch (pose chunks at N > 1): the per-launch totals of
+        # the capture are scaled by the ray count -- instructions and bytes per ray do not depend on how many frames a launch holds
+        f = float(rays_per_launch) / float(tj["rays_per_launch"])
+        tj = dict(tj)
+        for k in ("inst_executed", "dram_bytes_read", "dram_bytes_write", "dram_bytes_per_launch", "lts_t_bytes", "l1tex_t_bytes"):
+            if k in tj:
+                tj[k] = int(tj[k] * f)
+        tj.pop("kernel_ms_ncu", None)
+        tj["source"] = f"scaled x{f:.4f} by rays per launch from: " + str(tj.get("source"))
     return tj, None
 
 
@@ -333,7 +343,13 @@ class Leg:
             self.ctx.set_option("push_blocks", args.push_blocks)
         if args.gather_ramp:
             self.ctx.set_option("gather_ramp", args.gather_ramp)
+        if args.gather_taper:
+            self.ctx.set_option("gather_taper", args.gather_taper)
+        if args.push_mode is not None:
+            self.ctx.set_option("push_mode", args.push_mode)
         self.peer.enable()
+        if not args.gather_copy_self:
+            self.bufs = self.peer.local_out(self.P)        # compact straight into this rank's region of its own gather buffer
 
     def step(self):
         self.ctx.scan_enqueue(self.poses_d, self.intr, self.noise, self.bufs)
@@ -664,8 +680,9 @@ def run_ours(args):
             "run": {"numa_node_rank0": numa, "l2_persist_pct": int(args.l2_persist) if args.l2_persist is not None else ctx.default_l2_persist(),
                     "build_tag": tag, "host_threads": host_threads(),
                     "collective": ("none" if world == 1 else
-                                   f"all-gather over NVLink peer memory: each compacted pose chunk's xyz|label|frame_offset is pushed to all {world} ranks by an "
-                                   f"exchange kernel (16 B vector stores) while the next chunk is traversed; {args.gather_chunks} chunks, inside the step" if args.gather == "p2p" else
+                                   f"all-gather over NVLink peer memory: each compacted pose chunk's xyz|label|frame_offset is pushed to the other {world - 1} ranks by an "
+                                   f"exchange kernel (TMA bulk copies global -> shared -> peer; --push-mode 0: 16 B vector stores) while the next chunk is traversed; "
+                                   f"{args.gather_chunks} chunks, inside the step" if args.gather == "p2p" else
                                    f"NCCL all-gather of xyz|label|frame_offset blocks, {args.gather_chunks} chunks, overlapped with traversal, inside the step"),
                     "process_group": "none" if world == 1 else "nccl (barrier, all_reduce of timings and of the gather check)"},
             "frames_per_s": round(len(poses_all) / (ms_per_step * 1e-3), 1),
@@ -689,9 +706,16 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-        time.sleep(0.5 if rank == 0 else 0.0)              # NCCL's own log lines (NCCL_DEBUG=INFO) first, the JSON line last
     if rank == 0:
+        if world > 1:
+            time.sleep(1.0)                                # the other ranks' NCCL log lines (NCCL_DEBUG=INFO) first ...
         print(json.dumps(line), flush=True)
+        if world > 1:
+            # ... and the JSON line last: NCCL writes a closing line from a library destructor at process exit, after
+            # anything Python can print -- leave without running C-level exit handlers (everything is flushed and joined)
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(1 if bad else 0)
     return 1 if bad else 0
 
 
@@ -708,8 +732,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-per-frame", action="store_true", help="skip the per-frame call-pattern leg")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N>1: how the clouds are exchanged")
-    ap.add_argument("--gather-chunks", type=int, default=4, help="N>1: pose chunks per rank for the overlapped all-gather")
+    ap.add_argument("--gather-chunks", type=int, default=None, help="N>1: pose chunks per rank for the overlapped all-gather (default: 2 / 4 / 6 at 2 / 4 / 8 GPUs)")
+    ap.add_argument("--gather-copy-self", action="store_true", help="N>1: compact into private buffers and let the exchange kernel copy to the own gather buffer too (round-1 behaviour)")
     ap.add_argument("--gather-ramp", type=int, default=None, help="N>1: first chunk = regular chunk / ramp")
+    ap.add_argument("--gather-taper", type=int, default=3, help="N>1: last chunk = regular chunk / taper (its exchange is not hidden behind a traversal)")
+    ap.add_argument("--push-mode", type=int, default=None, help="N>1: exchange kernel, 0 = vector loads / stores, 1 = TMA bulk copies")
     ap.add_argument("--push-blocks", type=int, default=None, help="N>1: blocks per target of the exchange kernel")
     ap.add_argument("--e2e-chunk", type=int, default=None, help="poses per chunk of the pipelined e2e path")
     ap.add_argument("--no-numa-bind", action="store_true", help="N>1: do not pin each rank to its GPU's NUMA node")
@@ -721,6 +748,11 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=0, help="--impl reference: frames per step (0 = as many as fit --ref-budget)")
     ap.add_argument("--ref-budget", type=float, default=100.0, help="--impl reference: seconds of CPU work for the timed steps")
     args = ap.parse_args()
+    if args.gather_chunks is None:
+        n = max(args.gpus, int(os.environ.get("WORLD_SIZE", "1")))
+        args.gather_chunks = 2 if n <= 2 else 4 if n <= 4 else 6          # measured: profiles/r02h_scaling.md
+    if args.push_blocks is None and max(args.gpus, int(os.environ.get("WORLD_SIZE", "1"))) >= 8:
+        args.push_blocks = 96
     if args.impl == "reference":
         return run_reference(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))

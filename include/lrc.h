@@ -312,7 +312,9 @@ int lrc_kernel_times(lrc_ctx* ctx, double* h_trace_ms, double* h_compact_ms, int
  *   "persistent"    1 / 2: persistent warps that fetch 128-ray blocks by ticket instead of one block per 128 rays
  *   "block"         threads per traversal block (32 / 64 / 128)
  *   "chunk_rays"    rays per traversal chunk (bounds the 24 B/ray scratch)
- *   "gather_chunks", "gather_ramp", "push_blocks"   pose chunks / short first chunk / exchange blocks of the all-gather
+ *   "gather_chunks", "gather_ramp", "gather_taper", "push_blocks", "push_mode"   pose chunks / short first chunk / short
+ *                   last chunk / exchange blocks / exchange kernel (1 = TMA bulk copies, default; 0 = vector loads and stores)
+ *                   of the all-gather
  *   "kernel_timing" record CUDA events around k_trace and the compaction (lrc_kernel_times)
  *   "l2_persist"    percent of the device's maximum persisting-L2 set-aside reserved for an access-policy window over
  *                   the BVH records on every k_trace launch (0 = off, default); "l2_reset" demotes persisting lines now

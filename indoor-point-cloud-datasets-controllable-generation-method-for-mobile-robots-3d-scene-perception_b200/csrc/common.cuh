@@ -92,7 +92,9 @@ struct lrc_ctx {
     } gather;
     int64_t opt_gather_chunks = 4;
     int64_t opt_gather_ramp = 1;        // first gather chunk = regular chunk / ramp
-    int64_t opt_push_blocks = 16;       // blocks per target of the k_push exchange kernel
+    int64_t opt_gather_taper = 1;       // last gather chunk = regular chunk / taper
+    int64_t opt_push_blocks = 64;       // blocks in total of k_push_tma (push_mode 1) / blocks per target of k_push (push_mode 0; 16 measured best there)
+    int64_t opt_push_mode = 1;          // exchange kernel: 1 = k_push_tma (TMA bulk copies, default), 0 = k_push (vector loads / stores)
 
     // ---- planner support (plan.cu): binned vertex index ----
     bool ci_ready = false;

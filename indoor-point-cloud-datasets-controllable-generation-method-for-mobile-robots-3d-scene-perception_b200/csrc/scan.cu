@@ -634,11 +634,151 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_push(PushParams q, const __gri
     const int64_t tid = (int64_t)blockIdx.x * PUSH_THREADS + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * PUSH_THREADS;
     const long long gp = gt.point_base + a;
-    push_words(reinterpret_cast<const uint32_t*>(q.xyz + 3 * a), reinterpret_cast<uint32_t*>(gt.xyz[k] + 3 * gp), 3 * (b - a), tid, nthreads);
-    if (q.label) push_words(q.label + a, gt.label[k] + gp, b - a, tid, nthreads);
-    else for (int64_t i = tid; i < b - a; i += nthreads) gt.label[k][gp + i] = 0u;
+    // a scan whose outputs already ARE this rank's region of its own gather buffer (PeerGather.local_out) has nothing to
+    // copy to itself: one target less per step, and no second pass over the local cloud
+    if (gt.xyz[k] + 3 * gp != q.xyz + 3 * a)
+        push_words(reinterpret_cast<const uint32_t*>(q.xyz + 3 * a), reinterpret_cast<uint32_t*>(gt.xyz[k] + 3 * gp), 3 * (b - a), tid, nthreads);
+    if (q.label) {
+        if (gt.label[k] + gp != q.label + a) push_words(q.label + a, gt.label[k] + gp, b - a, tid, nthreads);
+    } else for (int64_t i = tid; i < b - a; i += nthreads) gt.label[k][gp + i] = 0u;
     for (int64_t f = tid; f < q.nf; f += nthreads) gt.frame_offset[k][gt.frame_base + q.f0 + f] = gt.point_base + q.frame_offset[q.f0 + f];
     if (q.last && tid == 0) gt.frame_offset[k][gt.frame_base + q.P] = gt.point_base + b;
+}
+
+// ---- the same exchange through the TMA engines (option "push_mode" = 1) ------------------------------------------------------
+// k_push moves every byte through registers: loads and stores of 64 x N blocks compete with k_trace for exactly the
+// resource that bounds it (the L1 / LSU data path; measured: k_trace 0.39 -> 0.53 ms per chunk at 4 GPUs while the
+// exchange runs).  Here ONE thread per block drives 1-D bulk copies: a 16 KB tile of the chunk's compacted stream goes
+// global -> shared (cp.async.bulk ... mbarrier::complete_tx) and from shared to EVERY target (cp.async.bulk.global.shared::cta,
+// peer memory over NVLink included) -- the tile is read from HBM once instead of once per target, no data touches a
+// register, and a handful of blocks keeps megabytes in flight.  Streams: the chunk's xyz bytes and label bytes; their
+// 16-byte-aligned middle goes through TMA, the (at most 15-byte) head and tail and the frame offsets through plain stores.
+constexpr int TMA_TILE = 16384;
+constexpr int TMA_STAGES = 4;
+constexpr int TMA_THREADS = 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra D;\n"
+        "bra W;\n"
+        "D:\n"
+        "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+
+struct TmaStream {
+    const char* src;        // first byte of the chunk's slice in the local compacted output
+    int64_t dst_off;        // byte offset of that slice inside every target's array
+    int64_t bytes;
+    int kind;               // 0 = xyz, 1 = label
+};
+
+__global__ void __launch_bounds__(TMA_THREADS) k_push_tma(PushParams q, const __grid_constant__ GatherTargets gt)
+{
+    extern __shared__ __align__(128) unsigned char tma_smem[];
+    __shared__ __align__(8) unsigned long long bars[TMA_STAGES];
+    const long long a = q.run[0], b = q.run[1];
+    const long long gp = gt.point_base + a;
+    TmaStream st[2];
+    st[0].src = reinterpret_cast<const char*>(q.xyz + 3 * a); st[0].dst_off = 12 * gp; st[0].bytes = 12 * (b - a); st[0].kind = 0;
+    st[1].src = reinterpret_cast<const char*>(q.label + a);   st[1].dst_off = 4 * gp;  st[1].bytes = q.label ? 4 * (b - a) : 0; st[1].kind = 1;
+    auto target_base = [&](int k, int kind) -> char* { return kind == 0 ? reinterpret_cast<char*>(gt.xyz[k]) : reinterpret_cast<char*>(gt.label[k]); };
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < TMA_STAGES; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bars[i])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    int64_t g0 = 0;       // tiles this block has pushed in earlier streams: stage and barrier parity continue from there
+    for (int sidx = 0; sidx < 2; ++sidx) {
+        const TmaStream& S = st[sidx];
+        if (S.bytes <= 0) continue;
+        // aligned middle [head, head + mid): source and destination are congruent modulo 16 when the rank's point base keeps
+        // the alignment (capacity a multiple of 4 points, which PeerGather guarantees); otherwise everything goes the slow way
+        int64_t head = (int64_t)((16u - (unsigned)((uintptr_t)S.src & 15u)) & 15u);
+        if (head > S.bytes) head = S.bytes;
+        bool congruent = true;
+        for (int k = 0; k < gt.n; ++k)
+            congruent = congruent && ((((uintptr_t)(target_base(k, S.kind) + S.dst_off)) & 15u) == (((uintptr_t)S.src) & 15u));
+        const int64_t mid = congruent ? ((S.bytes - head) & ~(int64_t)15) : 0;
+        if (!congruent) head = 0;
+        const int64_t n_tiles = (mid + TMA_TILE - 1) / TMA_TILE;
+        // tiles of this block: blockIdx.x, blockIdx.x + gridDim.x, ...
+        const int64_t mine = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        if (threadIdx.x == 0 && mine > 0) {
+            auto tile_bytes = [&](int64_t i) -> uint32_t {
+                const int64_t t = blockIdx.x + i * gridDim.x;
+                const int64_t left = mid - t * TMA_TILE;
+                return (uint32_t)(left < TMA_TILE ? left : TMA_TILE);
+            };
+            auto issue_load = [&](int64_t i) {
+                const int stage = (int)((g0 + i) % TMA_STAGES);
+                const int64_t t = blockIdx.x + i * gridDim.x;
+                const uint32_t nb = tile_bytes(i);
+                const uint32_t bar = smem_u32(&bars[stage]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(nb) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(smem_u32(tma_smem + stage * TMA_TILE)), "l"(S.src + head + t * TMA_TILE), "r"(nb), "r"(bar) : "memory");
+            };
+            static_assert(TMA_STAGES >= 3, "the pipeline keeps TMA_STAGES - 2 loads ahead");
+            const int ahead = TMA_STAGES - 2;
+            for (int64_t i = 0; i < ahead && i < mine; ++i) issue_load(i);
+            for (int64_t i = 0; i < mine; ++i) {
+                if (i + ahead < mine) {
+                    // the stage of tile i + ahead was last read by the stores of tile i + ahead - STAGES = i - 2: at most the most
+                    // recent store group may still be reading shared memory
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    issue_load(i + ahead);
+                }
+                const int stage = (int)((g0 + i) % TMA_STAGES);
+                mbar_wait(smem_u32(&bars[stage]), (unsigned)(((g0 + i) / TMA_STAGES) & 1));
+                const int64_t t = blockIdx.x + i * gridDim.x;
+                const uint32_t nb = tile_bytes(i);
+                for (int k = 0; k < gt.n; ++k) {
+                    char* dst = target_base(k, S.kind) + S.dst_off + head + t * TMA_TILE;
+                    if (dst == S.src + head + t * TMA_TILE) continue;       // this rank's own region already holds the data
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 :: "l"(dst), "r"(smem_u32(tma_smem + stage * TMA_TILE)), "r"(nb) : "memory");
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        // head, tail (and everything, when not congruent): plain 4-byte stores by block 0
+        if (blockIdx.x == 0) {
+            const int64_t tail0 = head + mid;
+            const int64_t n_words = (head + (S.bytes - tail0)) >> 2;
+            for (int64_t i = threadIdx.x; i < n_words * gt.n; i += TMA_THREADS) {
+                const int k = (int)(i / n_words);
+                const int64_t wd = i - (int64_t)k * n_words;
+                const int64_t off = wd < (head >> 2) ? 4 * wd : tail0 + 4 * (wd - (head >> 2));
+                char* dst = target_base(k, S.kind) + S.dst_off + off;
+                if (dst != S.src + off) *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(S.src + off);
+            }
+        }
+        g0 += mine;
+        __syncthreads();      // the next stream reuses the stages and their barriers
+    }
+    if (!q.label && blockIdx.x == 0)
+        for (int64_t i = threadIdx.x; i < (b - a) * gt.n; i += TMA_THREADS) gt.label[i / (b - a)][gp + i % (b - a)] = 0u;
+    if (blockIdx.x == gridDim.x - 1) {
+        for (int64_t i = threadIdx.x; i < q.nf * gt.n; i += TMA_THREADS) {
+            const int k = (int)(i / q.nf);
+            const int64_t f = i - (int64_t)k * q.nf;
+            gt.frame_offset[k][gt.frame_base + q.f0 + f] = gt.point_base + q.frame_offset[q.f0 + f];
+        }
+        if (q.last && threadIdx.x < gt.n) gt.frame_offset[threadIdx.x][gt.frame_base + q.P] = gt.point_base + b;
+    }
+    // make the bulk stores of this block globally visible before the kernel (and with it the stream-ordered event) completes
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ---- host-side launch plumbing -----------------------------------------------------------------------
@@ -812,18 +952,36 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
     if (frames_per_chunk < 1) frames_per_chunk = 1;
     if (frames_per_chunk > P) frames_per_chunk = P;   // size the scratch by the largest REAL chunk (a one-frame call must not reserve 2^26 rays)
     if (MODE == MODE_RAYS) frames_per_chunk = P;   // a single explicit frame
-    if (gather && MODE != MODE_RAYS && ctx->opt_gather_chunks > 1) {
-        const int64_t want = (P + ctx->opt_gather_chunks - 1) / ctx->opt_gather_chunks;
-        if (want >= 1 && want < frames_per_chunk) frames_per_chunk = want;
+    std::vector<int64_t> chunk_start;              // first frame of every chunk, closed by P
+    if (gather && MODE != MODE_RAYS && ctx->opt_gather_chunks > 1 && P > 1) {
+        // With gather targets chunk c is exchanged while chunk c+1 is traversed.  Two things are exposed: the wait for the
+        // first chunk (the exchange, not the traversal, is the long pole at 4+ GPUs: NVLink ingress) and the exchange of the
+        // last chunk.  "gather_ramp" / "gather_taper" make the first / last chunk 1/ramp / 1/taper of a regular one.
+        const int64_t C = ctx->opt_gather_chunks < P ? ctx->opt_gather_chunks : P;
+        std::vector<double> wgt((size_t)C, 1.0);
+        if (C > 1) { wgt[0] = 1.0 / (double)ctx->opt_gather_ramp; wgt[(size_t)C - 1] = 1.0 / (double)ctx->opt_gather_taper; }
+        double sum = 0.0;
+        for (double x : wgt) sum += x;
+        double acc = 0.0;
+        int64_t f = 0;
+        for (int64_t c = 0; c < C && f < P; ++c) {
+            chunk_start.push_back(f);
+            acc += wgt[(size_t)c];
+            int64_t end = c == C - 1 ? P : (int64_t)((double)P * acc / sum + 0.5);
+            if (end <= f) end = f + 1;
+            if (end - f > frames_per_chunk) end = f + frames_per_chunk;     // never beyond the scratch bound
+            if (end > P) end = P;
+            f = end;
+        }
+        while (f < P) { chunk_start.push_back(f); f += frames_per_chunk < P - f ? frames_per_chunk : P - f; }
+    } else {
+        for (int64_t f = 0; f < P; f += frames_per_chunk) chunk_start.push_back(f);
     }
-    // With gather targets the exchange, not the traversal, is the long pole at 4+ GPUs (NVLink ingress): start it early
-    // with a short first chunk ("gather_ramp" = its size as a fraction 1/ramp of a regular chunk; 1 = uniform chunks).
-    int64_t first_chunk = frames_per_chunk;
-    if (gather && MODE != MODE_RAYS && ctx->opt_gather_ramp > 1 && P > frames_per_chunk) {
-        first_chunk = frames_per_chunk / ctx->opt_gather_ramp;
-        if (first_chunk < 1) first_chunk = 1;
-    }
-    const int64_t n_chunks = 1 + (P > first_chunk ? (P - first_chunk + frames_per_chunk - 1) / frames_per_chunk : 0);
+    chunk_start.push_back(P);
+    const int64_t n_chunks = (int64_t)chunk_start.size() - 1;
+    frames_per_chunk = 1;
+    for (int64_t c = 0; c < n_chunks; ++c)
+        if (chunk_start[(size_t)c + 1] - chunk_start[(size_t)c] > frames_per_chunk) frames_per_chunk = chunk_start[(size_t)c + 1] - chunk_start[(size_t)c];
     const bool piped = n_chunks > 1;
     const int n_slots = piped ? 2 : 1;
     const int64_t chunk_rays = frames_per_chunk * N;
@@ -876,9 +1034,8 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
     }
     for (int64_t c = 0; c < n_chunks; ++c) {
         const int slot = piped ? (int)(c & 1) : 0;
-        const int64_t f0 = c == 0 ? 0 : first_chunk + (c - 1) * frames_per_chunk;
-        const int64_t want_nf = c == 0 ? first_chunk : frames_per_chunk;
-        const int64_t nf = (f0 + want_nf <= P) ? want_nf : P - f0;
+        const int64_t f0 = chunk_start[(size_t)c];
+        const int64_t nf = chunk_start[(size_t)c + 1] - f0;
         const int64_t n = nf * N;
         const int64_t nb = (n + TB - 1) / TB;
         float4* hp = (float4*)((char*)ctx->scratch + slot_bytes * slot);
@@ -915,8 +1072,18 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
             PushParams pp;
             pp.xyz = out->xyz; pp.label = q.out.label; pp.frame_offset = out->frame_offset; pp.run = run + c;
             pp.f0 = f0; pp.nf = nf; pp.P = P; pp.last = last ? 1 : 0;
-            k_push<<<dim3((unsigned)ctx->opt_push_blocks, (unsigned)gt.n), PUSH_THREADS, 0, aux>>>(pp, gt);
-            LRC_CHECK_LAUNCH(ctx, "k_push");
+            if (ctx->opt_push_mode == 1) {
+                static bool attr_set = false;
+                if (!attr_set) {
+                    LRC_CUDA(ctx, cudaFuncSetAttribute(k_push_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_STAGES * TMA_TILE));
+                    attr_set = true;
+                }
+                k_push_tma<<<(unsigned)ctx->opt_push_blocks, TMA_THREADS, TMA_STAGES * TMA_TILE, aux>>>(pp, gt);
+                LRC_CHECK_LAUNCH(ctx, "k_push_tma");
+            } else {
+                k_push<<<dim3((unsigned)ctx->opt_push_blocks, (unsigned)gt.n), PUSH_THREADS, 0, aux>>>(pp, gt);
+                LRC_CHECK_LAUNCH(ctx, "k_push");
+            }
         }
         if (timing) { LRC_CUDA(ctx, cudaEventRecord(ctx->kt_events[4 * c + 3], aux)); ctx->kt_used = (size_t)(4 * (c + 1)); }
     }
@@ -1181,7 +1348,9 @@ extern "C" int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value)
         ctx->opt_top_levels = value;
         return LRC_OK;
     }
+    if (!strcmp(key, "gather_taper")) { if (value < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "gather_taper must be >= 1"); ctx->opt_gather_taper = value; return LRC_OK; }
     if (!strcmp(key, "gather_ramp")) { if (value < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "gather_ramp must be >= 1"); ctx->opt_gather_ramp = value; return LRC_OK; }
+    if (!strcmp(key, "push_mode")) { if (value < 0 || value > 1) return lrc_fail(ctx, LRC_ERR_INVALID, "push_mode must be 0 (LSU kernel) or 1 (TMA bulk copies)"); ctx->opt_push_mode = value; return LRC_OK; }
     if (!strcmp(key, "push_blocks")) { if (value < 1 || value > 1024) return lrc_fail(ctx, LRC_ERR_INVALID, "push_blocks must be in [1, 1024]"); ctx->opt_push_blocks = value; return LRC_OK; }
     if (!strcmp(key, "gather_chunks")) { if (value < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "gather_chunks must be >= 1"); ctx->opt_gather_chunks = value; return LRC_OK; }
     if (!strcmp(key, "block")) {

@@ -249,7 +249,7 @@ class PeerGather:
         self.rank, self.world = world_info(group)
         if self.world > nat.Gather.xyz.size // C.sizeof(C.c_void_p):
             raise ValueError("PeerGather supports at most 16 ranks")
-        self.cap, self.pmax = int(cap_per_rank), int(frames_per_rank)
+        self.cap, self.pmax = (int(cap_per_rank) + 3) // 4 * 4, int(frames_per_rank)      # a multiple of 4 points: every rank's region keeps 16-byte alignment (TMA bulk copies)
         w = self.world
         self.o_lab = (w * self.cap * 12 + 255) // 256 * 256
         self.o_off = (self.o_lab + w * self.cap * 4 + 255) // 256 * 256
@@ -290,6 +290,18 @@ class PeerGather:
         self.buffer = torch.as_tensor(_RawCudaBuffer(self.local_ptr, self.nbytes), device=ctx.device)
         if w > 1:
             dist.barrier(group=group)
+
+    def local_out(self, frames: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        """Output buffers for ``Context.scan_enqueue`` that ARE this rank's region of its own gather buffer: the compaction
+        then writes the local cloud straight to its final place and the exchange kernel skips the copy to itself (one
+        target and one pass over the local cloud less per step).  ``off`` is a private (P+1,) array -- the gathered
+        offsets carry each rank's point base and are written by the exchange kernel."""
+        xyz, lab, _ = self.views()
+        nf = self.pmax if frames is None else int(frames)
+        if getattr(self, "_local_inc", None) is None:
+            self._local_inc = torch.empty(self.cap, dtype=torch.float64, device=self.ctx.device)
+        return {"xyz": xyz[self.rank], "incident": self._local_inc, "prim": None, "label": lab[self.rank], "ray": None,
+                "off": torch.zeros(nf + 1, dtype=torch.int64, device=self.ctx.device)}
 
     def enable(self):
         import ctypes as C

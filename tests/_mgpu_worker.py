@@ -47,8 +47,12 @@ def main():
     pg = PeerGather(engine.ctx, cap_per_rank=6 * 64000, frames_per_rank=6)
     pg.enable()
     engine.ctx.set_option("gather_chunks", 3)
-    for ramp, blocks in ((1, 16), (2, 3)):          # uniform chunks, then a short first chunk and few exchange blocks
+    # uniform chunks; a short first chunk and few exchange blocks; a short last chunk; both short
+    # ... and the same through the TMA exchange kernel (push_mode 1)
+    for ramp, taper, blocks, mode in ((1, 1, 16, 0), (2, 1, 3, 0), (1, 3, 16, 0), (4, 4, 8, 0), (1, 1, 16, 1), (2, 3, 3, 1), (1, 1, 1, 1)):
+        engine.ctx.set_option("push_mode", mode)
         engine.ctx.set_option("gather_ramp", ramp)
+        engine.ctx.set_option("gather_taper", taper)
         engine.ctx.set_option("push_blocks", blocks)
         pg.buffer.zero_()
         torch.cuda.synchronize()
@@ -62,14 +66,29 @@ def main():
         # the reference's frame is (points, incident angles): the angles are recomputed on arrival, bit for bit
         assert np.array_equal(got["incident"], ref["incident"]), ramp
         dist.barrier()
+    # compaction straight into this rank's region of its own gather buffer (no copy to itself), both exchange kernels
+    for mode in (0, 1):
+        engine.ctx.set_option("push_mode", mode)
+        pg.buffer.zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+        bufs = pg.local_out(sl.stop - sl.start)
+        engine.ctx.scan(poses12[sl.start:sl.stop], intr, local_noise, bufs=bufs)
+        pg.synchronize()
+        got = pg.assemble_numpy(poses_all=poses12)
+        for k in ("frame_offset", "points", "label", "incident"):
+            assert np.array_equal(got[k], ref[k]), ("local_out", mode, k)
+        dist.barrier()
+    engine.ctx.set_option("push_mode", 0)
     # a scan of more frames than this rank's offset region holds must be refused, not spill into the neighbour's region
     try:
-        engine.simulate(poses12[:7], intr, noise=local_noise)
+        engine.simulate(poses12[:7], lrc.Indoor8LineLidarIntrinsics(max_range=5.0))      # 7 x 16000 rays fit, 7 + 1 offsets do not
         raise AssertionError("expected LRC_ERR_CAPACITY")
     except RuntimeError as e:
         assert "frame_capacity" in str(e), e
     pg.disable()
     engine.ctx.set_option("gather_ramp", 1)
+    engine.ctx.set_option("gather_taper", 1)
     a, b = ref["frame_offset"][sl.start], ref["frame_offset"][sl.stop]
     assert np.array_equal(local["points"], ref["points"][a:b]) and np.array_equal(local["incident"], ref["incident"][a:b])
     pg.close()

@@ -145,16 +145,28 @@ def test_gathered_record_is_complete_and_regions_are_guarded(lrc):
     try:
         pg.enable()
         ctx.set_option("gather_chunks", 2)
-        ref = engine.simulate(poses, intr, noise=noise).numpy()
+        for mode in (0, 1):                                   # exchange kernel: vector loads / stores, TMA bulk copies
+            ctx.set_option("push_mode", mode)
+            pg.buffer.zero_()
+            ref = engine.simulate(poses, intr, noise=noise).numpy()
+            pg.synchronize()
+            got = pg.assemble_numpy(poses_all=poses)
+            for k in ("frame_offset", "points", "label", "incident"):
+                assert np.array_equal(got[k], ref[k]), (mode, k)
+        assert got["incident"].dtype == np.float64 and len(got["incident"]) > 10000
+        # compaction straight into this rank's own region (no self copy by the exchange kernel): same bits
+        pg.buffer.zero_()
+        direct = ctx.scan(poses, intr, noise, bufs=pg.local_out(5)).numpy()
         pg.synchronize()
         got = pg.assemble_numpy(poses_all=poses)
         for k in ("frame_offset", "points", "label", "incident"):
-            assert np.array_equal(got[k], ref[k]), k
-        assert got["incident"].dtype == np.float64 and len(got["incident"]) > 10000
+            assert np.array_equal(got[k], ref[k]), ("local_out", k)
+        assert np.array_equal(direct["points"], ref["points"]) and np.array_equal(direct["incident"], ref["incident"])
         more = lrc.poses_from_waypoints([lrc.Waypoint(1.5 + 0.4 * k, 3.2, 1.0, 0.0) for k in range(6)])
         with pytest.raises(RuntimeError, match="frame_capacity"):
             engine.simulate(more[:6], lrc.Indoor8LineLidarIntrinsics(max_range=5.0))
     finally:
         pg.disable()
         ctx.set_option("gather_chunks", 4)
+        ctx.set_option("push_mode", 0)
         pg.close()

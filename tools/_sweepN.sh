@@ -1,0 +1,8 @@
+N=$1
+shift
+for cfg in "$@"; do set -- $cfg
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 3 --no-cpu --extra none --push-mode $1 --push-blocks $2 --gather-chunks $3 2>/dev/null | tail -1 | python -c "
+import sys,json
+d=json.loads(sys.stdin.read())
+print('N $N push_mode $1 blocks $2 chunks $3', d['value'], d['ms_per_step'], d['gather_bit_identical'], d['exchange']['nvlink_ingest_gbs_over_exchange_kernels'], d['roofline']['kernel_ms'], d['roofline'].get('compact_plus_exchange_ms'), d['e2e']['ms_per_step'])"
+done
