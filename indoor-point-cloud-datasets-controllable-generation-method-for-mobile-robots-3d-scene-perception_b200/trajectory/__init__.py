@@ -5,6 +5,7 @@ coverage planner produces the waypoints (its occupancy / collision / connectivit
 """
 from .trajectory_generator import (TrajectoryQuality, Waypoint, polyline_waypoints, poses_from_waypoints, shard_range)
 from .auto_trajectory_generator import AutoTrajectoryGenerator, RoomAnalysis, TrajectoryCandidate
+from .collision_detector import CollisionDetector, FurnitureInfo
 
 __all__ = ["Waypoint", "TrajectoryQuality", "poses_from_waypoints", "polyline_waypoints", "shard_range",
-           "AutoTrajectoryGenerator", "RoomAnalysis", "TrajectoryCandidate"]
+           "AutoTrajectoryGenerator", "RoomAnalysis", "TrajectoryCandidate", "CollisionDetector", "FurnitureInfo"]

@@ -78,6 +78,8 @@ class AutoTrajectoryGenerator:
         self.min_waypoints = 40
         self._device = device
         self._ctx = None
+        from .collision_detector import CollisionDetector
+        self.collision_detector = CollisionDetector(robot_radius)          # reference :51
 
     # ---- GPU plumbing ---------------------------------------------------------------------------------------
     @property
@@ -362,3 +364,13 @@ class AutoTrajectoryGenerator:
             "room_analysis": {"free_space_points": len(ra.free_space_points), "obstacle_points": len(ra.obstacle_points),
                               "room_dimensions": ra.dimensions.tolist(), "room_center": ra.center.tolist()},
         }
+
+    # ---- furniture records (reference :693-704; the reference stores them and never queries them while planning) ----
+    def add_furniture(self, furniture) -> None:
+        self.collision_detector.add_furniture(furniture)
+
+    def add_furniture_from_mesh(self, mesh, name: str, category: str = "unknown") -> None:
+        self.collision_detector.add_furniture_from_mesh(mesh, name, category)
+
+    def clear_furniture(self) -> None:
+        self.collision_detector.clear_furniture()
