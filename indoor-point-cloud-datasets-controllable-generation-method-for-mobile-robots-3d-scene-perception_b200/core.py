@@ -196,6 +196,45 @@ class ScanResult:
 
 
 # --------------------------------------------------------------------------------------------------
+# page-locked result buffers that are handed out as numpy arrays
+# --------------------------------------------------------------------------------------------------
+class _PinnedLease:
+    """One page-locked buffer on loan.  ``array`` wraps it as a numpy array whose base keeps this lease alive; when the last
+    such array is dropped the buffer returns to its pool (CPython reference counting makes that immediate)."""
+    __slots__ = ("pool", "tensor", "ptr")
+
+    def __init__(self, pool, tensor):
+        self.pool, self.tensor, self.ptr = pool, tensor, tensor.data_ptr()
+
+    def array(self, dtype, count: int) -> np.ndarray:
+        buf = (C.c_char * (np.dtype(dtype).itemsize * count)).from_address(self.ptr)
+        buf._lease = self                       # ndarray -> memoryview -> ctypes array -> lease -> pinned tensor
+        return np.frombuffer(buf, dtype=dtype, count=count)
+
+    def __del__(self):
+        pool = self.pool
+        if pool is not None and pool.free is not None:
+            pool.free.append(self.tensor)
+
+
+class _PinnedPool:
+    """At most ``max_items`` page-locked buffers of ``item_bytes`` each, allocated on demand (cudaHostAlloc is slow: a miss
+    costs about a millisecond, a hit nothing)."""
+
+    def __init__(self, item_bytes: int, max_items: int = 8):
+        self.item_bytes, self.max_items, self.count = int(item_bytes), int(max_items), 0
+        self.free: Optional[list] = []
+
+    def acquire(self) -> Optional[_PinnedLease]:
+        if self.free:
+            return _PinnedLease(self, self.free.pop())
+        if self.count >= self.max_items:
+            return None
+        self.count += 1
+        return _PinnedLease(self, torch.empty(self.item_bytes, dtype=torch.uint8).pin_memory())
+
+
+# --------------------------------------------------------------------------------------------------
 # context
 # --------------------------------------------------------------------------------------------------
 def _ptr(t: Optional[torch.Tensor]):
@@ -434,12 +473,15 @@ class Context:
         return st[0][:m].numpy().copy(), st[1][:m].numpy().copy()
 
     # ---- trajectory scan with HOST results: chunked, D2H overlapped with the next chunks' kernels ----
-    def alloc_host_buffers(self, capacity: int, frames: int, labels: bool = True, extras: bool = False) -> dict:
-        """Pinned host staging for ``scan_to_host`` (allocate once, reuse across calls)."""
+    def alloc_host_buffers(self, capacity: int, frames: int, labels: bool = True, extras: bool = False, incident: bool = True) -> dict:
+        """Pinned host staging for ``scan_to_host`` (allocate once, reuse across calls).  ``incident=False`` leaves the
+        incident angles on the device (8 of the 24 bytes per point that cross PCIe): they are a pure function of point and
+        pose, the per-frame statistics that consume them run on the GPU (``frame_statistics``), and
+        ``lrc_incident_angles`` reproduces them bit for bit from the points whenever they are wanted after all."""
         cap = max(1, int(capacity))
         h = {
             "points": torch.empty((cap, 3), dtype=torch.float32).pin_memory(),
-            "incident": torch.empty(cap, dtype=torch.float64).pin_memory(),
+            "incident": torch.empty(cap, dtype=torch.float64).pin_memory() if incident else None,
             "label": torch.empty(cap, dtype=torch.int32).pin_memory() if labels else None,
             "prim_id": torch.empty(cap, dtype=torch.int32).pin_memory() if extras else None,
             "ray_idx": torch.empty(cap, dtype=torch.int32).pin_memory() if extras else None,
@@ -480,8 +522,9 @@ class Context:
                 d = single_axis_desc(intr)
                 nat.check(self._h, self._lib.lrc_scan_single_axis_host(self._h, pp, P, C.byref(d), nzp, C.byref(out), chunk, C.byref(total)))
         m = int(total.value)
-        res = {"points": host["points"][:m].numpy(), "incident": host["incident"][:m].numpy(),
-               "frame_offset": host["frame_offset"][:P + 1].numpy(), "num_points": m}
+        res = {"points": host["points"][:m].numpy(), "frame_offset": host["frame_offset"][:P + 1].numpy(), "num_points": m}
+        if host.get("incident") is not None:
+            res["incident"] = host["incident"][:m].numpy()
         for k in ("label", "prim_id", "ray_idx"):
             if host.get(k) is not None:
                 res[k] = host[k][:m].numpy().view(np.uint32)
@@ -489,21 +532,32 @@ class Context:
 
     def scan_frame_to_host(self, pose, intr, noise: Optional[NoiseConfig] = None):
         """ONE frame, host in / host out, one library call and one synchronisation: the reference's per-waypoint call
-        pattern (s3dis_simulator.py:254-263).  The pose goes up from host memory, points and incident angles come back
-        through page-locked staging kept by this context (``lrc_scan_*_host`` copies a small frame at capacity right
-        behind its kernels instead of waiting for the point count first) and are returned as fresh numpy arrays.
-        -> (points (m,3) float32, incident (m,) float64)"""
+        pattern (s3dis_simulator.py:254-263).  The pose goes up from host memory; points and incident angles are copied
+        by the device straight into page-locked buffers that BECOME the returned numpy arrays (``_PinnedPool``: a buffer
+        goes back to the pool when the caller drops the array, so a loop that consumes frames one by one never copies on
+        the host; a caller that keeps every frame exhausts the pool and gets ordinary arrays filled from staging).
+        ``lrc_scan_*_host`` copies a small frame at capacity right behind its kernels instead of waiting for the point
+        count first.  -> (points (m,3) float32, incident (m,) float64)"""
         dual = is_dual_axis(intr)
         d = dual_axis_desc(intr) if dual else single_axis_desc(intr)
-        n = d.num_lines * d.points_per_line if dual else d.H * d.W
-        st = getattr(self, "_frame_host", None)
-        if st is None or st[0].shape[0] < n:
-            cap = max(n, 1)
-            st = (torch.empty((cap, 3), dtype=torch.float32).pin_memory(), torch.empty(cap, dtype=torch.float64).pin_memory(),
-                  torch.zeros(2, dtype=torch.int64).pin_memory())
-            self._frame_host = st
+        n = max(1, d.num_lines * d.points_per_line if dual else d.H * d.W)
+        pools = getattr(self, "_frame_pools", None)
+        if pools is None or pools[0].item_bytes < 12 * n:
+            pools = (_PinnedPool(12 * n), _PinnedPool(8 * n), torch.zeros(2, dtype=torch.int64).pin_memory())
+            self._frame_pools = pools
+        la, lb = pools[0].acquire(), pools[1].acquire()
+        zero_copy = la is not None and lb is not None
+        if not zero_copy:
+            la = lb = None
+            st = getattr(self, "_frame_host", None)
+            if st is None or st[0].shape[0] < n:
+                st = (torch.empty((n, 3), dtype=torch.float32).pin_memory(), torch.empty(n, dtype=torch.float64).pin_memory())
+                self._frame_host = st
+            p_xyz, p_inc = st[0].data_ptr(), st[1].data_ptr()
+        else:
+            p_xyz, p_inc = la.ptr, lb.ptr
         pose_h = np.ascontiguousarray(pose, dtype=np.float64).reshape(16)
-        out = nat.Out(C.c_void_p(st[0].data_ptr()), C.c_void_p(st[1].data_ptr()), None, None, None, C.c_void_p(st[2].data_ptr()), int(st[0].shape[0]))
+        out = nat.Out(C.c_void_p(p_xyz), C.c_void_p(p_inc), None, None, None, C.c_void_p(pools[2].data_ptr()), n)
         nz = noise.struct() if noise is not None else None
         total = C.c_int64(0)
         fn = self._lib.lrc_scan_dual_axis_host if dual else self._lib.lrc_scan_single_axis_host
@@ -513,6 +567,8 @@ class Context:
         m = int(total.value)
         if m == 0:
             return np.zeros((0, 3), np.float32), np.empty(0)
+        if zero_copy:
+            return la.array(np.float32, 3 * m).reshape(m, 3), lb.array(np.float64, m)
         return st[0][:m].numpy().copy(), st[1][:m].numpy().copy()
 
     def set_mesh_host(self, verts: np.ndarray, tris: np.ndarray, labels: Optional[np.ndarray] = None) -> None:

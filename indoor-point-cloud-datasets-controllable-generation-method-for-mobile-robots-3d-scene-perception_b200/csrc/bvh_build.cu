@@ -570,6 +570,21 @@ extern "C" int lrc_set_mesh(lrc_ctx* ctx, const float* verts, int64_t V, const i
         ctx->nodes = (float4*)ctx->bvh_block;
         ctx->tris = (float4*)((char*)ctx->bvh_block + nodes_bytes);
         ctx->bvh_bytes = nodes_bytes + tris_bytes;
+        // a linear float4 texture over the node records (format 0 / 2: 4 texels per record) for the kernels that split
+        // their node loads between the LSU and the texture pipe; beyond the linear-texture limit those kernels are not used
+        if (ctx->nodes_tex) { cudaDestroyTextureObject(ctx->nodes_tex); ctx->nodes_tex = 0; }
+        if (nodes_bytes / sizeof(float4) <= ((size_t)1 << 27)) {
+            cudaResourceDesc rd;
+            memset(&rd, 0, sizeof rd);
+            rd.resType = cudaResourceTypeLinear;
+            rd.res.linear.devPtr = ctx->nodes;
+            rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+            rd.res.linear.sizeInBytes = nodes_bytes;
+            cudaTextureDesc td;
+            memset(&td, 0, sizeof td);
+            td.readMode = cudaReadModeElementType;
+            if (cudaCreateTextureObject(&ctx->nodes_tex, &rd, &td, nullptr) != cudaSuccess) { ctx->nodes_tex = 0; cudaGetLastError(); }
+        }
     }
     if ((size_t)T > ctx->labels_cap) {
         if (ctx->labels) LRC_CUDA(ctx, cudaFree(ctx->labels));

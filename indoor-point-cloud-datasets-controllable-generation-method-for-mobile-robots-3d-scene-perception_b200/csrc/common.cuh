@@ -30,6 +30,7 @@ struct lrc_ctx {
     bool has_labels = false;
     int64_t T = 0, V = 0;
     float4* nodes = nullptr;      // num_nodes x 4 float4 (64 B records)
+    cudaTextureObject_t nodes_tex = 0;   // the same records behind the texture path (tune bits 3 / 4): its own L1TEX data pipe and write-back
     float4* tris = nullptr;       // T x 3 float4 (48 B records, Morton order): (v0|orig id) (e1|0) (e2|0)
     uint32_t* labels = nullptr;   // T, original triangle order
     int64_t opt_leaf_size = 2;    // triangles per leaf built by the NEXT lrc_set_mesh (1..8); 2 measured best

@@ -216,14 +216,14 @@ __device__ __forceinline__ bool trace_one(const RayGen& g, const FrameMath& fm, 
                                           const float4* __restrict__ tris, int64_t idx, int has_tris, float4* __restrict__ hp,
                                           double* __restrict__ inc_out, float* __restrict__ t_hit, uint32_t* __restrict__ prim_id,
                                           const float4* s_top, int top_n, int stack_levels, const NodeQ& nq, int root, unsigned& nn,
-                                          unsigned& nt, unsigned& nr, unsigned& nh)
+                                          unsigned& nt, unsigned& nr, unsigned& nh, cudaTextureObject_t ntex = 0)
 {
     int64_t pose; int r;
     Ray ray = gen_ray<MODE>(g, idx, pose, r);
     float t = LRC_INF;
     uint32_t id = LRC_MISS_ID;
     if (ray.keep && has_tris) {
-        trace_ray<VARIANT, COUNT>(nodes, tris, s_top, top_n, stack_levels, nq, root, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, t, id, nn, nt);
+        trace_ray<VARIANT, COUNT>(nodes, tris, s_top, top_n, stack_levels, nq, root, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, t, id, nn, nt, ntex);
         nr += 1;
         nh += id != LRC_MISS_ID;
     }
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, (VARIANT & 4) ? 16 : (VARIANT &
 k_trace(RayGen g, FrameMath fm, const float4* __restrict__ nodes, const float4* __restrict__ tris, int64_t n, int has_tris,
         float4* __restrict__ hp, double* __restrict__ inc_out, unsigned* __restrict__ block_count, float* __restrict__ t_hit,
         uint32_t* __restrict__ prim_id, unsigned long long* counters, const float4* __restrict__ top_table, int top_n,
-        int stack_levels, const __grid_constant__ NodeQ nq, int root, int tile_shift)
+        int stack_levels, const __grid_constant__ NodeQ nq, int root, int tile_shift, cudaTextureObject_t ntex)
 {
     extern __shared__ float4 s_top[];
     constexpr bool PERSIST = (VARIANT & 256) != 0;
@@ -273,7 +273,7 @@ k_trace(RayGen g, FrameMath fm, const float4* __restrict__ nodes, const float4* 
             for (unsigned k = 0; k < tiles_per_block; ++k) {
                 const int64_t idx = (((int64_t)b << tile_shift) + k) * 32 + lane_id();
                 bool keep = false;
-                if (idx < n) keep = trace_one<MODE, COUNT, OUT_DENSE, VARIANT>(g, fm, nodes, tris, idx, has_tris, hp, inc_out, t_hit, prim_id, s_top, top_n, stack_levels, nq, root, nn, nt, nr, nh);
+                if (idx < n) keep = trace_one<MODE, COUNT, OUT_DENSE, VARIANT>(g, fm, nodes, tris, idx, has_tris, hp, inc_out, t_hit, prim_id, s_top, top_n, stack_levels, nq, root, nn, nt, nr, nh, ntex);
                 kept += __popc(__ballot_sync(0xffffffffu, keep));
             }
             if (!OUT_DENSE && lane_id() == 0) block_count[b] = kept;
@@ -281,7 +281,7 @@ k_trace(RayGen g, FrameMath fm, const float4* __restrict__ nodes, const float4* 
     } else {
         const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         bool keep = false;
-        if (idx < n) keep = trace_one<MODE, COUNT, OUT_DENSE, VARIANT>(g, fm, nodes, tris, idx, has_tris, hp, inc_out, t_hit, prim_id, s_top, top_n, stack_levels, nq, root, nn, nt, nr, nh);
+        if (idx < n) keep = trace_one<MODE, COUNT, OUT_DENSE, VARIANT>(g, fm, nodes, tris, idx, has_tris, hp, inc_out, t_hit, prim_id, s_top, top_n, stack_levels, nq, root, nn, nt, nr, nh, ntex);
         if (NOBAR) {
             // per-warp keep counts meet in shared memory; the warp that arrives last publishes the block's count.  No warp
             // waits for the block's slowest ray: its slot is free for the next block's warps as soon as it is done.
@@ -845,9 +845,13 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
     const float4* top_table = ctx->top_table;
     const NodeQ nq = ctx->nodeq;
     const int root = ctx->root;
+    const cudaTextureObject_t ntex = ctx->nodes_tex;
     // the resident tree's record format selects the kernel family; the variant option tunes the float-format kernels
     int64_t variant = ctx->node_format == 1 ? 37 : ctx->node_format == 2 ? ((ctx->opt_variant & 64) ? 193 : 129) : ctx->opt_variant;
-    if (variant == 193 && ctx->opt_tune) variant |= (ctx->opt_tune & 7) << 10;     // bits 10..12: prefetch, no barrier, streaming stores
+    if (variant == 193 && ctx->opt_tune) {
+        variant |= (ctx->opt_tune & 7) << 10;     // bits 10..12: prefetch, no barrier, streaming stores
+        if (ctx->nodes_tex) variant |= ((ctx->opt_tune >> 3) & 3) << 13;      // bits 13..14: record halves fetched through the texture pipe
+    }
     int tile_shift = 0;
     if (ctx->opt_persistent && (variant == 1 || variant == 65 || variant == 129 || variant == 193)) {
         variant |= 256;
@@ -864,7 +868,7 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3((unsigned)TB); cfg.stream = stream;
     cudaError_t le = cudaSuccess;
 #define LRC_LAUNCH_TRACE(COUNT, VARIANT) \
-    le = cudaLaunchKernelEx(&cfg, k_trace<MODE, COUNT, DENSE, VARIANT>, g, fm, nodes, tris, n, has_tris, hp, inc, block_count, t_hit, prim, counters, top_table, top_n, stack_levels, nq, root, tile_shift)
+    le = cudaLaunchKernelEx(&cfg, k_trace<MODE, COUNT, DENSE, VARIANT>, g, fm, nodes, tris, n, has_tris, hp, inc, block_count, t_hit, prim, counters, top_table, top_n, stack_levels, nq, root, tile_shift, ntex)
     if (ctx->counting) {
         switch (variant) {
             case 0: LRC_LAUNCH_TRACE(true, 0); break;
@@ -887,6 +891,9 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
             case 4289: LRC_LAUNCH_TRACE(true, 4289); break;
             case 6337: LRC_LAUNCH_TRACE(true, 6337); break;
             case 7361: LRC_LAUNCH_TRACE(true, 7361); break;
+            case 10433: LRC_LAUNCH_TRACE(true, 10433); break;
+            case 18625: LRC_LAUNCH_TRACE(true, 18625); break;
+            case 26817: LRC_LAUNCH_TRACE(true, 26817); break;
             default: LRC_LAUNCH_TRACE(true, 3); break;
         }
     } else {
@@ -911,6 +918,9 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
             case 4289: LRC_LAUNCH_TRACE(false, 4289); break;
             case 6337: LRC_LAUNCH_TRACE(false, 6337); break;
             case 7361: LRC_LAUNCH_TRACE(false, 7361); break;
+            case 10433: LRC_LAUNCH_TRACE(false, 10433); break;
+            case 18625: LRC_LAUNCH_TRACE(false, 18625); break;
+            case 26817: LRC_LAUNCH_TRACE(false, 26817); break;
             default: LRC_LAUNCH_TRACE(false, 3); break;
         }
     }
@@ -1213,6 +1223,7 @@ extern "C" void lrc_destroy(lrc_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->nodes_tex) cudaDestroyTextureObject(ctx->nodes_tex);
     cudaFree(ctx->bvh_block); cudaFree(ctx->labels); cudaFree(ctx->top_table);
     cudaFree(ctx->scratch); cudaFree(ctx->scratch2); cudaFree(ctx->tables); cudaFree(ctx->d_counters);
     cudaFree(ctx->host_dev); cudaFree(ctx->mesh_dev); cudaFree(ctx->post_scratch);
@@ -1370,7 +1381,8 @@ extern "C" int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value)
     }
     if (!strcmp(key, "warp_packet")) { ctx->opt_warp_packet = value != 0; return LRC_OK; }
     if (!strcmp(key, "tune")) {
-        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 6 && value != 7) return lrc_fail(ctx, LRC_ERR_INVALID, "tune must be 0, 1, 2, 4, 6 or 7");
+        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 6 && value != 7 && value != 10 && value != 18 && value != 26)
+            return lrc_fail(ctx, LRC_ERR_INVALID, "tune must be 0, 1, 2, 4, 6, 7, 10, 18 or 26");
         ctx->opt_tune = value;
         return LRC_OK;
     }

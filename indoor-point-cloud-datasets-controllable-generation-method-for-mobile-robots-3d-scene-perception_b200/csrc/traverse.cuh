@@ -330,13 +330,28 @@ __device__ __forceinline__ void prefetch_link(const float4* __restrict__ nodes, 
     asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
 }
 
-template <bool COUNT, class STACK, bool PF = false>
+// TEXM: which quarters of the record come through the texture pipe instead of the LSU (bit 0: Z and links, bit 1: A and B).
+// ncu: the LSU data pipe and its register write-back are the busiest units of k_trace (77 % / 67 %) while the texture
+// pipe of the same L1TEX unit idles; a linear float4 texture over the node array lets the two halves of a record return
+// through different pipes.
+template <bool COUNT, class STACK, bool PF = false, int TEXM = 0>
 __device__ __forceinline__ int inner_step_p(const float4* __restrict__ nodes, int cur, const RaySlabP& s, float best_t,
-                                            STACK& stack, int& sp, unsigned& n_nodes, const float4* __restrict__ tris = nullptr)
+                                            STACK& stack, int& sp, unsigned& n_nodes, const float4* __restrict__ tris = nullptr,
+                                            cudaTextureObject_t ntex = 0)
 {
     const float4* np = nodes + 4 * (int64_t)cur;
-    const float4 A = __ldg(np + 0), B = __ldg(np + 1), Z = __ldg(np + 2);
-    const float2 L = __ldg(reinterpret_cast<const float2*>(np + 3));
+    float4 A, B, Z;
+    float2 L;
+    if (TEXM & 2) { A = tex1Dfetch<float4>(ntex, 4 * cur + 0); B = tex1Dfetch<float4>(ntex, 4 * cur + 1); }
+    else { A = __ldg(np + 0); B = __ldg(np + 1); }
+    if (TEXM & 1) {
+        Z = tex1Dfetch<float4>(ntex, 4 * cur + 2);
+        const float4 L4 = tex1Dfetch<float4>(ntex, 4 * cur + 3);
+        L = make_float2(L4.x, L4.y);
+    } else {
+        Z = __ldg(np + 2);
+        L = __ldg(reinterpret_cast<const float2*>(np + 3));
+    }
     if (COUNT) ++n_nodes;
     const float2 naxy = make_float2(-s.axy.x, -s.axy.y), nazz = make_float2(-s.azz.x, -s.azz.y);
     const float2 tc0 = ffma2(make_float2(A.x, A.y), s.ixy, s.nxy);      // child 0: (x, y) slab centres
@@ -360,10 +375,10 @@ __device__ __forceinline__ int inner_step_p(const float4* __restrict__ nodes, in
     return StackOps<STACK>::pop(stack, sp, best_t, nullptr, 0);
 }
 
-template <bool COUNT, class STACK, bool PF = false>
+template <bool COUNT, class STACK, bool PF = false, int TEXM = 0>
 __device__ __forceinline__ void trace_loop_p(const float4* __restrict__ nodes, const float4* __restrict__ tris, int root, float ox,
                                              float oy, float oz, float dx, float dy, float dz, float& best_t, uint32_t& best_id,
-                                             unsigned& n_nodes, unsigned& n_tris)
+                                             unsigned& n_nodes, unsigned& n_tris, cudaTextureObject_t ntex = 0)
 {
     best_t = LRC_INF;
     best_id = LRC_MISS_ID;
@@ -372,7 +387,7 @@ __device__ __forceinline__ void trace_loop_p(const float4* __restrict__ nodes, c
     int sp = 0;
     int cur = root;
     while (cur != LRC_SENTINEL) {
-        while (cur >= 0) cur = inner_step_p<COUNT, STACK, PF>(nodes, cur, s, best_t, stack, sp, n_nodes, tris);
+        while (cur >= 0) cur = inner_step_p<COUNT, STACK, PF, TEXM>(nodes, cur, s, best_t, stack, sp, n_nodes, tris, ntex);
         if (cur != LRC_SENTINEL) {
             leaf_test(tris, cur, ox, oy, oz, dx, dy, dz, best_t, best_id, n_tris);
             cur = StackOps<STACK>::pop(stack, sp, best_t, nullptr, 0);
@@ -645,10 +660,11 @@ template <int VARIANT, bool COUNT>
 __device__ __forceinline__ void trace_ray(const float4* __restrict__ nodes, const float4* __restrict__ tris,
                                           const float4* smem, int top_n, int stack_levels, const NodeQ& nq, int root, float ox,
                                           float oy, float oz, float dx, float dy, float dz, float& best_t,
-                                          uint32_t& best_id, unsigned& n_nodes, unsigned& n_tris)
+                                          uint32_t& best_id, unsigned& n_nodes, unsigned& n_tris, cudaTextureObject_t ntex = 0)
 {
     if (VARIANT & 128) {
-        if (VARIANT & 1024) trace_loop_p<COUNT, StackCull, true>(nodes, tris, root, ox, oy, oz, dx, dy, dz, best_t, best_id, n_nodes, n_tris);
+        if (VARIANT & (8192 | 16384)) trace_loop_p<COUNT, StackCull, false, ((VARIANT >> 13) & 3)>(nodes, tris, root, ox, oy, oz, dx, dy, dz, best_t, best_id, n_nodes, n_tris, ntex);
+        else if (VARIANT & 1024) trace_loop_p<COUNT, StackCull, true>(nodes, tris, root, ox, oy, oz, dx, dy, dz, best_t, best_id, n_nodes, n_tris);
         else if (VARIANT & 64) trace_loop_p<COUNT, StackCull>(nodes, tris, root, ox, oy, oz, dx, dy, dz, best_t, best_id, n_nodes, n_tris);
         else trace_loop_p<COUNT, StackLocal>(nodes, tris, root, ox, oy, oz, dx, dy, dz, best_t, best_id, n_nodes, n_tris);
     } else if (VARIANT & 32) {

@@ -170,3 +170,29 @@ def test_gathered_record_is_complete_and_regions_are_guarded(lrc):
         ctx.set_option("gather_chunks", 4)
         ctx.set_option("push_mode", 0)
         pg.close()
+
+
+def test_per_frame_results_stay_valid_when_kept(lrc):
+    """The per-waypoint call returns arrays backed by pooled page-locked buffers (8 per array kind).  A caller that keeps
+    every frame (the reference's simulator does, s3dis_simulator.py:287) must still own independent, intact arrays: the
+    pool falls back to ordinary copies once it is exhausted, and a dropped frame gives its buffer back."""
+    engine = lrc.RaycastEngineGPU()
+    mesh = lrc.synthetic.box_room(target_tris=20000, seed=1)
+    engine.set_mesh(mesh)
+    for intr in (lrc.Indoor8LineLidarIntrinsics(max_range=30.0), lrc.DualAxisLidarIntrinsics.create_blk2go_dual_axis()):
+        poses = lrc.poses_from_waypoints([lrc.Waypoint(1.5 + 0.3 * k, 3.2 + 0.05 * k, 1.0, 0.1 * k) for k in range(13)])
+        dual = hasattr(intr, "num_vertical_lines")
+        lidars = [lrc.create_lidar(intr, p) for p in poses]
+        kept = [engine.lidar_intersect_mesh(l, mesh) for l in lidars]                   # 13 > 8 frames alive at once
+        for k, (pts, inc) in enumerate(kept):
+            nz = lidars[k].noise_config() if dual else None
+            ref = engine.simulate(poses[k][None], intr, noise=nz).numpy()
+            assert pts.dtype == np.float32 and inc.dtype == np.float64 and pts.flags.writeable
+            assert np.array_equal(pts, ref["points"]) and np.array_equal(inc, ref["incident"]), k
+        first = kept[0][0].copy()
+        kept[5][0][:] = 0.0                                                              # frames do not alias each other
+        assert np.array_equal(kept[0][0], first) and not np.array_equal(kept[4][0], kept[5][0])
+        del kept
+        again = engine.lidar_intersect_mesh(lidars[3], mesh)                             # buffers were returned and are reused
+        ref = engine.simulate(poses[3][None], intr, noise=lidars[3].noise_config() if dual else None).numpy()
+        assert np.array_equal(again[0], ref["points"]) and np.array_equal(again[1], ref["incident"])

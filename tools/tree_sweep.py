@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--formats", default="0", help="node formats: 0 = 64 B centre/half, 1 = 32 B 16-bit, 2 = 64 B paired (packed FMA)")
     ap.add_argument("--persistent", default="0", help="0 / 1: persistent warps over 32-ray tiles")
     ap.add_argument("--rpt", default="1", help="rays per thread (1, 2, 4); > 1 needs format 2")
+    ap.add_argument("--block", default="128", help="threads per traversal block (32 / 64 / 128)")
     ap.add_argument("--wp", default="0", help="0 / 1: warp-packet traversal (format 2)")
     ap.add_argument("--tune", default="0", help="format-2 kernel tuning bits: 1 prefetch, 2 no block barrier, 4 streaming scratch stores")
     ap.add_argument("--poses", type=int, default=None)
@@ -70,44 +71,46 @@ def main():
         build_ms = e0.elapsed_time(e1)
         info = ctx.bvh_info()
         for var, pers, rpt, tune, wp in itertools.product(ints(args.variants), ints(args.persistent), ints(args.rpt), ints(args.tune), ints(args.wp)):
-            if rpt > 1 and (fmt != 2 or pers or var != ints(args.variants)[-1]):
-                continue
-            if tune and (fmt != 2 or pers or rpt > 1 or var != 65):
-                continue
-            if wp and (fmt != 2 or pers or rpt > 1 or tune):
-                continue
-            ctx.set_option("warp_packet", wp)
-            ctx.set_option("tune", tune)
-            ctx.set_option("variant", var)
-            ctx.set_option("persistent", pers)
-            ctx.set_option("rays_per_thread", rpt)
-            ctx.set_counting(True)
-            ctx.counters(reset=True)
-            ctx.scan_enqueue(poses_d, intr, noise, bufs)
-            cnt = ctx.counters(reset=True)
-            ctx.set_counting(False)
-            ctx.set_option("kernel_timing", 1)
-            tr, cp = [], []
-            for r in range(args.reps + 2):
-                flush.fill_(r & 255)
+          for blk in ints(args.block):
+                if rpt > 1 and (fmt != 2 or pers or var != ints(args.variants)[-1]):
+                    continue
+                if tune and (fmt != 2 or pers or rpt > 1 or var != 65):
+                    continue
+                if wp and (fmt != 2 or pers or rpt > 1 or tune):
+                    continue
+                ctx.set_option("warp_packet", wp)
+                ctx.set_option("block", blk)
+                ctx.set_option("tune", tune)
+                ctx.set_option("variant", var)
+                ctx.set_option("persistent", pers)
+                ctx.set_option("rays_per_thread", rpt)
+                ctx.set_counting(True)
+                ctx.counters(reset=True)
                 ctx.scan_enqueue(poses_d, intr, noise, bufs)
-                torch.cuda.synchronize()
-                kt = ctx.kernel_times()
-                if r >= 2:
-                    tr.append(kt["trace_ms"])
-                    cp.append(kt["compact_ms"])
-            ctx.set_option("kernel_timing", 0)
-            m = int(bufs["off"][-1].item())
-            sig = (m, int(bufs["prim"][:m].to(torch.int64).sum().item()), float(bufs["xyz"][:m].double().sum().item()))
-            if ref is None:
-                ref = sig
-            rays = max(1, cnt["rays"])
-            print(json.dumps({"workload": args.workload, "quality": q, "leaf_size": leaf, "ploc_radius": rad if q else None, "node_format": fmt, "variant": var, "persistent": pers, "rays_per_thread": rpt, "tune": tune, "warp_packet": wp,
-                              "build_ms": round(build_ms, 3), "height": info["max_depth"], "sah": round(info["sah_cost"], 2),
-                              "nodes_per_ray": round(cnt["nodes_visited"] / rays, 2), "tris_per_ray": round(cnt["tris_tested"] / rays, 2),
-                              "trace_ms": round(float(np.mean(tr)), 4), "trace_ms_min": round(float(np.min(tr)), 4),
-                              "compact_ms": round(float(np.mean(cp)), 4), "Mrays_s_trace": round(P * n_frame / np.mean(tr) / 1e3, 1),
-                              "same_output": sig == ref}), flush=True)
+                cnt = ctx.counters(reset=True)
+                ctx.set_counting(False)
+                ctx.set_option("kernel_timing", 1)
+                tr, cp = [], []
+                for r in range(args.reps + 2):
+                    flush.fill_(r & 255)
+                    ctx.scan_enqueue(poses_d, intr, noise, bufs)
+                    torch.cuda.synchronize()
+                    kt = ctx.kernel_times()
+                    if r >= 2:
+                        tr.append(kt["trace_ms"])
+                        cp.append(kt["compact_ms"])
+                ctx.set_option("kernel_timing", 0)
+                m = int(bufs["off"][-1].item())
+                sig = (m, int(bufs["prim"][:m].to(torch.int64).sum().item()), float(bufs["xyz"][:m].double().sum().item()))
+                if ref is None:
+                    ref = sig
+                rays = max(1, cnt["rays"])
+                print(json.dumps({"workload": args.workload, "quality": q, "leaf_size": leaf, "ploc_radius": rad if q else None, "node_format": fmt, "variant": var, "persistent": pers, "rays_per_thread": rpt, "tune": tune, "warp_packet": wp, "block": blk,
+                                  "build_ms": round(build_ms, 3), "height": info["max_depth"], "sah": round(info["sah_cost"], 2),
+                                  "nodes_per_ray": round(cnt["nodes_visited"] / rays, 2), "tris_per_ray": round(cnt["tris_tested"] / rays, 2),
+                                  "trace_ms": round(float(np.mean(tr)), 4), "trace_ms_min": round(float(np.min(tr)), 4),
+                                  "compact_ms": round(float(np.mean(cp)), 4), "Mrays_s_trace": round(P * n_frame / np.mean(tr) / 1e3, 1),
+                                  "same_output": sig == ref}), flush=True)
 
 
 if __name__ == "__main__":
