@@ -9,6 +9,7 @@ import csv
 import io
 import json
 import os
+import re
 import subprocess
 import sys
 
@@ -53,7 +54,7 @@ def main():
         raise SystemExit("no k_trace launch in the report")
     d = best[1]
     u = dict(zip(hdr, units))
-    e = {"tris": tris, "rays_per_launch": rays, "build_tag": tag, "kernel": d["Kernel Name"].split("(")[0].replace("void <unnamed>::", "")[:60],
+    e = {"tris": tris, "rays_per_launch": rays, "build_tag": tag, "kernel": re.sub(r"\((int|bool)\)", "", d["Kernel Name"]).split("(")[0].replace("void <unnamed>::", "").replace("void ", "")[:60],
          "grid": best[0]}
     for name, metric in PICK.items():
         if metric in d and d[metric] != "":

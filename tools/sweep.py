@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE config 5: ray-count sweep x mesh-size sweep with the roofline fraction per point.
 
-    python tools/sweep.py [--tris 1e4,1e5,1e6,1e7] [--rays 1e5,1e6,1e7,1e8,1e9] [--out profiles/r01_sweep_c5]
+    python tools/sweep.py [--tris 1e4,1e5,1e6,1e7] [--rays 1e5,1e6,1e7,1e8,1e9] [--out profiles/r02_sweep_c5]
 
 Rays are 32-line frames (128 000 rays) x poses on the synthetic office at each triangle count; rays are generated
 in-kernel and the trajectory is processed in pose chunks that reuse one output buffer, so memory stays bounded at 1e9
@@ -28,13 +28,26 @@ def main():
     ap.add_argument("--tris", default="1e4,1e5,1e6,1e7")
     ap.add_argument("--rays", default="1e5,1e6,1e7,1e8,1e9")
     ap.add_argument("--chunk-poses", type=int, default=400)
-    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r01_sweep_c5"))
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r02_sweep_c5"))
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     ctx = lrc.RaycastEngineGPU(device=0).ctx
     intr = lrc.Indoor8LineLidarIntrinsics.create_dense_32line()
     n_frame = lrc.rays_per_frame(intr)
     peak, peak_src = bench.measured_peak_gbs()
+    # warp instructions per ray of k_trace from the committed ncu captures of the same sensor and mesh (profiles/traffic.json):
+    # where one exists for a mesh size, the point also gets the fraction of the issue-slot peak (the binding resource)
+    inst_per_ray = {}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        for key in ("c2", "sweep_1e7"):                     # the captures taken with this sensor on this mesh family
+            e = tj.get(key)
+            if e and e.get("build_tag") == bench.build_tag(ctx):
+                inst_per_ray[int(e["tris"])] = e["inst_executed"] / e["rays_per_launch"]
+    except Exception:
+        pass
+    props = torch.cuda.get_device_properties(dev)
+    issue_peak = props.multi_processor_count * 4 * 1965e6
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     bufs, _ = ctx._alloc_out(args.chunk_poses * n_frame, args.chunk_poses)
     rows = []
@@ -95,7 +108,8 @@ def main():
                    "Mrays_s": round(rays / (tr + cp) / 1e3, 1), "Mrays_s_trace": round(rays / tr / 1e3, 1),
                    "nodes_per_ray": round(npr, 2), "tris_per_ray": round(tpr, 2), "hit_fraction": round(hit, 4),
                    "bytes_per_ray": round(b_trace, 1), "achieved_gbs": round(rays * b_trace / tr / 1e6, 1),
-                   "frac_of_hbm_peak": round(rays * b_trace / tr / 1e6 / peak, 3), "chunks": len(chunks)}
+                   "algorithmic_over_hbm_peak": round(rays * b_trace / tr / 1e6 / peak, 3), "chunks": len(chunks),
+                   "issue_frac": round(inst_per_ray[int(len(f))] * rays / (tr * 1e-3) / issue_peak, 3) if int(len(f)) in inst_per_ray else None}
             rows.append(row)
             print(json.dumps(row), flush=True)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
@@ -106,14 +120,17 @@ def main():
         fh.write("# BASELINE config 5 -- ray-count x mesh-size sweep on one B200 (tools/sweep.py)\n\n"
                  f"32-line frames (128 000 rays) on the synthetic office; HBM peak = {peak} GB/s ({peak_src}); CUDA events "
                  "inside the library around k_trace and around k_scan_counts+k_compact, summed over pose chunks, best of "
-                 "the timed repetitions, L2 flushed before each.  `frac` = algorithmic bytes of k_trace (64 B per node record + "
-                 "48 B per triangle record fetched + 24 B scratch written, per ray) / k_trace time / HBM peak; values above 1 mean "
-                 "the records were served from L1/L2, not HBM.\n\n"
-                 "| tris | BVH MB | build ms | rays | k_trace ms | compact ms | Mrays/s (path) | Mrays/s (k_trace) | nodes/ray | tris/ray | B/ray | GB/s alg. | frac |\n"
-                 "|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|\n")
+                 "the timed repetitions, L2 flushed before each.  `alg/HBM` = algorithmic bytes of k_trace (64 B per node record + "
+                 "48 B per triangle record fetched + 24 B scratch written, per ray) / k_trace time / HBM peak -- SURVEY 8d's byte model; "
+                 "values above 1 mean the records were served from L1/L2, not HBM, so it is NOT an HBM utilisation.  `issue` = warp "
+                 "instructions (per-ray count of the committed ncu capture of that mesh size, profiles/traffic.json) / k_trace time / "
+                 "(SMs x 4 x 1965 MHz): the fraction of the resource that bounds the kernel; blank where no capture of that mesh exists.\n\n"
+                 "| tris | BVH MB | build ms | rays | k_trace ms | compact ms | Mrays/s (path) | Mrays/s (k_trace) | nodes/ray | tris/ray | B/ray | GB/s alg. | alg/HBM | issue |\n"
+                 "|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|\n")
         for r in rows:
             fh.write(f"| {r['tris']} | {r['bvh_mb']} | {r['build_ms']} | {r['rays']:.3g} | {r['trace_ms']} | {r['compact_ms']} | {r['Mrays_s']} | "
-                     f"{r['Mrays_s_trace']} | {r['nodes_per_ray']} | {r['tris_per_ray']} | {r['bytes_per_ray']} | {r['achieved_gbs']} | {r['frac_of_hbm_peak']} |\n")
+                     f"{r['Mrays_s_trace']} | {r['nodes_per_ray']} | {r['tris_per_ray']} | {r['bytes_per_ray']} | {r['achieved_gbs']} | {r['algorithmic_over_hbm_peak']} | "
+                     f"{'' if r['issue_frac'] is None else r['issue_frac']} |\n")
 
 
 if __name__ == "__main__":
