@@ -1,3 +1,7 @@
+#!/bin/bash
+# Exchange-kernel / chunk-plan sweep on N GPUs of one box (profiles/r02h_scaling.md):
+#     gpurun --gpus N -- bash tools/exchange_sweep.sh N "<push_mode> <push_blocks> <gather_chunks>" ...
+# push_mode 0 = k_push (vector loads / stores), 1 = k_push_tma (TMA bulk copies).  One short line per configuration.
 N=$1
 shift
 for cfg in "$@"; do set -- $cfg
