@@ -963,13 +963,25 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
     if (frames_per_chunk > P) frames_per_chunk = P;   // size the scratch by the largest REAL chunk (a one-frame call must not reserve 2^26 rays)
     if (MODE == MODE_RAYS) frames_per_chunk = P;   // a single explicit frame
     std::vector<int64_t> chunk_start;              // first frame of every chunk, closed by P
-    if (gather && MODE != MODE_RAYS && ctx->opt_gather_chunks > 1 && P > 1) {
-        // With gather targets chunk c is exchanged while chunk c+1 is traversed.  Two things are exposed: the wait for the
-        // first chunk (the exchange, not the traversal, is the long pole at 4+ GPUs: NVLink ingress) and the exchange of the
-        // last chunk.  "gather_ramp" / "gather_taper" make the first / last chunk 1/ramp / 1/taper of a regular one.
-        const int64_t C = ctx->opt_gather_chunks < P ? ctx->opt_gather_chunks : P;
+    // Pose chunks: chunk c is compacted (and, with gather targets, exchanged) on the auxiliary stream while chunk c+1 is
+    // traversed.  Without gather targets ("scan_chunks" / "scan_taper") this hides the HBM-bound compaction behind k_trace,
+    // which leaves DRAM idle; only a whole trajectory of at least ~1M rays per chunk is cut.
+    int64_t want_chunks = 1, ramp = 1, taper = 1;
+    if (MODE != MODE_RAYS && P > 1) {
+        if (gather) { want_chunks = ctx->opt_gather_chunks; ramp = ctx->opt_gather_ramp; taper = ctx->opt_gather_taper; }
+        else {
+            want_chunks = ctx->opt_scan_chunks; taper = ctx->opt_scan_taper;
+            const int64_t by_size = total / ((int64_t)1 << 20);
+            if (want_chunks > by_size) want_chunks = by_size;
+        }
+    }
+    if (want_chunks > 1) {
+        // With gather targets two things are exposed: the wait for the first chunk (the exchange, not the traversal, is the
+        // long pole at 4+ GPUs: NVLink ingress) and the exchange of the last chunk.  "gather_ramp" / "gather_taper" make the
+        // first / last chunk 1/ramp / 1/taper of a regular one.
+        const int64_t C = want_chunks < P ? want_chunks : P;
         std::vector<double> wgt((size_t)C, 1.0);
-        if (C > 1) { wgt[0] = 1.0 / (double)ctx->opt_gather_ramp; wgt[(size_t)C - 1] = 1.0 / (double)ctx->opt_gather_taper; }
+        if (C > 1) { wgt[0] = 1.0 / (double)ramp; wgt[(size_t)C - 1] = 1.0 / (double)taper; }
         double sum = 0.0;
         for (double x : wgt) sum += x;
         double acc = 0.0;
@@ -1359,6 +1371,8 @@ extern "C" int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value)
         ctx->opt_top_levels = value;
         return LRC_OK;
     }
+    if (!strcmp(key, "scan_chunks")) { if (value < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "scan_chunks must be >= 1"); ctx->opt_scan_chunks = value; return LRC_OK; }
+    if (!strcmp(key, "scan_taper")) { if (value < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "scan_taper must be >= 1"); ctx->opt_scan_taper = value; return LRC_OK; }
     if (!strcmp(key, "gather_taper")) { if (value < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "gather_taper must be >= 1"); ctx->opt_gather_taper = value; return LRC_OK; }
     if (!strcmp(key, "gather_ramp")) { if (value < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "gather_ramp must be >= 1"); ctx->opt_gather_ramp = value; return LRC_OK; }
     if (!strcmp(key, "push_mode")) { if (value < 0 || value > 1) return lrc_fail(ctx, LRC_ERR_INVALID, "push_mode must be 0 (LSU kernel) or 1 (TMA bulk copies)"); ctx->opt_push_mode = value; return LRC_OK; }
