@@ -310,7 +310,8 @@ int lrc_kernel_times(lrc_ctx* ctx, double* h_trace_ms, double* h_compact_ms, int
  *   "compact_nodes" 1: squeeze the never-read records of collapsed subtrees out of the node array (half the node bytes)
  *   "rays_per_thread" 1 (default), 2, 4: adjacent rays per thread of the scan kernels (format 2 only; measured slower)
  *   "persistent"    1 / 2: persistent warps that fetch 128-ray blocks by ticket instead of one block per 128 rays
- *   "block"         threads per traversal block (32 / 64 / 128)
+ *   "block"         threads per traversal block (32 / 64 / 128); 0 (default) = by the size of the call: 32 up to 2^16 rays,
+ *                   64 up to 2^18, 128 beyond
  *   "chunk_rays"    rays per traversal chunk (bounds the 24 B/ray scratch)
  *   "gather_chunks", "gather_ramp", "gather_taper", "push_blocks", "push_mode"   pose chunks / short first chunk / short
  *                   last chunk / exchange blocks / exchange kernel (1 = TMA bulk copies, default; 0 = vector loads and stores)

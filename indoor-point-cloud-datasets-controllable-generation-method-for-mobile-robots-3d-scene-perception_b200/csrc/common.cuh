@@ -140,7 +140,8 @@ struct lrc_ctx {
     int64_t opt_tune = 2;               // format-2 kernel: bit 0 prefetch pushed records, bit 1 no block barrier (default), bit 2 streaming scratch stores
     int64_t opt_persistent = 0;         // 1: persistent warps over 32-ray tiles (VARIANT bit 8) instead of one block per 128 rays
     int num_sms = 148;
-    int64_t opt_block = 128;            // threads per traversal block
+    int64_t opt_block = 0;              // threads per traversal block (32 / 64 / 128); 0 = by the size of the call
+    int cur_block = 128;                // block size of the scan call being enqueued
     int64_t opt_chunk_rays = 1 << 26;   // rays per traversal/epilogue chunk (bounds scratch: 16 B per ray)
     int64_t opt_variant = 65;           // traversal kernel variant: while-while loop + stack entries culled at pop time (bit 6);
                                         // with node format 2 the packed-FMA loop (bit 7) is selected automatically

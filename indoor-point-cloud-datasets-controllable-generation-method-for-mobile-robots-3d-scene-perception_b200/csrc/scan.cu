@@ -793,8 +793,16 @@ int ensure_counters(lrc_ctx* ctx)
 
 // rays per thread of the scan kernels: > 1 needs the paired node records (format 2) and 128-ray compaction blocks
 inline int packet_rays(const lrc_ctx* ctx) { return ctx->node_format == 2 ? (int)ctx->opt_rays_per_thread : 1; }
-inline bool warp_packets(const lrc_ctx* ctx) { return ctx->opt_warp_packet && ctx->node_format == 2 && ctx->opt_block == TRACE_THREADS && packet_rays(ctx) == 1; }
-inline int scan_block_threads(const lrc_ctx* ctx) { return packet_rays(ctx) > 1 ? TRACE_THREADS : (int)ctx->opt_block; }
+inline bool warp_packets(const lrc_ctx* ctx) { return ctx->opt_warp_packet && ctx->node_format == 2 && packet_rays(ctx) == 1; }
+// Threads per traversal block (= rays per keep count of the compaction).  "block" = 0 (default) picks by the size of the
+// call: a one-frame call of 16 000 rays is 125 blocks of 128 threads on 148 SMs -- one warp per scheduler and nothing to hide
+// latency with -- so small calls use smaller blocks (measured: tools/small_frame_block.py); trajectories use 128.
+inline int scan_block_threads(const lrc_ctx* ctx, int64_t total_rays)
+{
+    if (packet_rays(ctx) > 1 || warp_packets(ctx)) return TRACE_THREADS;
+    if (ctx->opt_block) return (int)ctx->opt_block;
+    return total_rays <= (int64_t)1 << 16 ? 32 : total_rays <= (int64_t)1 << 18 ? 64 : TRACE_THREADS;
+}
 
 template <int MODE, bool DENSE>
 int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, float4* hp, double* inc, unsigned* block_count,
@@ -821,7 +829,7 @@ int launch_trace(lrc_ctx* ctx, const RayGen& g, const FrameMath& fm, int64_t n, 
         LRC_CHECK_LAUNCH(ctx, "k_trace_w");
         return LRC_OK;
     }
-    const int TB = DENSE ? TRACE_THREADS : (int)ctx->opt_block;
+    const int TB = DENSE ? TRACE_THREADS : ctx->cur_block;
     unsigned grid = (unsigned)((n + TB - 1) / TB);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
@@ -1007,7 +1015,8 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
     const bool piped = n_chunks > 1;
     const int n_slots = piped ? 2 : 1;
     const int64_t chunk_rays = frames_per_chunk * N;
-    const int TB = scan_block_threads(ctx);
+    const int TB = scan_block_threads(ctx, total);
+    ctx->cur_block = TB;
     const int64_t max_blocks = (chunk_rays + TB - 1) / TB;
     const bool want_inc = out->incident_deg != nullptr && max_range >= 0.0;
     const size_t hp_bytes = align_up(sizeof(float4) * (size_t)chunk_rays, 256);
@@ -1379,7 +1388,7 @@ extern "C" int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value)
     if (!strcmp(key, "push_blocks")) { if (value < 1 || value > 1024) return lrc_fail(ctx, LRC_ERR_INVALID, "push_blocks must be in [1, 1024]"); ctx->opt_push_blocks = value; return LRC_OK; }
     if (!strcmp(key, "gather_chunks")) { if (value < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "gather_chunks must be >= 1"); ctx->opt_gather_chunks = value; return LRC_OK; }
     if (!strcmp(key, "block")) {
-        if (value != 32 && value != 64 && value != 128) return lrc_fail(ctx, LRC_ERR_INVALID, "block must be 32, 64 or 128");
+        if (value != 0 && value != 32 && value != 64 && value != 128) return lrc_fail(ctx, LRC_ERR_INVALID, "block must be 0 (by call size), 32, 64 or 128");
         ctx->opt_block = value;
         return LRC_OK;
     }
