@@ -1104,10 +1104,9 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
             pp.xyz = out->xyz; pp.label = q.out.label; pp.frame_offset = out->frame_offset; pp.run = run + c;
             pp.f0 = f0; pp.nf = nf; pp.P = P; pp.last = last ? 1 : 0;
             if (ctx->opt_push_mode == 1) {
-                static bool attr_set = false;
-                if (!attr_set) {
+                if (!ctx->push_tma_ready) {      // per context (= per device): the opt-in to 64 KB of dynamic shared memory
                     LRC_CUDA(ctx, cudaFuncSetAttribute(k_push_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_STAGES * TMA_TILE));
-                    attr_set = true;
+                    ctx->push_tma_ready = true;
                 }
                 k_push_tma<<<(unsigned)ctx->opt_push_blocks, TMA_THREADS, TMA_STAGES * TMA_TILE, aux>>>(pp, gt);
                 LRC_CHECK_LAUNCH(ctx, "k_push_tma");

@@ -59,6 +59,17 @@ def test_c2_full_trajectory_properties(engine, lrc, office, office_poses):
         r = out["ray_idx"][off[f]:off[f + 1]].astype(np.int64)
         assert np.all(np.diff(r) > 0) and r.max() < 128000
     assert np.array_equal(out["label"], office.triangle_labels[out["prim_id"]])
+    # pose chunks on one GPU (compaction of chunk c behind the traversal of c+1; option, default off) and the warp-packet kernel
+    for opts in ({"scan_chunks": 3, "scan_taper": 3}, {"warp_packet": 1}):
+        for k, v in opts.items():
+            engine.ctx.set_option(k, v)
+        try:
+            alt = engine.simulate(office_poses, intr).numpy()
+        finally:
+            for k in opts:
+                engine.ctx.set_option(k, 1 if k.startswith("scan") else 0)
+        for k in ("points", "incident", "prim_id", "label", "ray_idx", "frame_offset"):
+            assert np.array_equal(alt[k], out[k]), (opts, k)
     a = engine.simulate(office_poses[:50], intr).numpy()
     b = engine.simulate(office_poses[50:], intr).numpy()
     for k in ("points", "incident", "prim_id", "label", "ray_idx"):
