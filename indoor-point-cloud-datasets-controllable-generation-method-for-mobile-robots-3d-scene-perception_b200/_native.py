@@ -64,6 +64,12 @@ class FrameStats(C.Structure):          # lrc_frame_stats
                 ("range_mean", C.c_double), ("range_std", C.c_double)]
 
 
+class GatherWire(C.Structure):         # lrc_gather_wire
+    _fields_ = [("enabled", C.c_int32), ("self_index", C.c_int32), ("t", C.c_void_p * 16), ("ray_idx", C.c_void_p * 16),
+                ("ready", C.c_void_p * 16), ("all_poses", C.c_void_p), ("rank_pose0", C.c_int64 * 16), ("rank_frames", C.c_int64 * 16),
+                ("rank_point_base", C.c_int64 * 16), ("rank_frame_base", C.c_int64 * 16)]
+
+
 class BvhInfo(C.Structure):             # lrc_bvh_info
     _fields_ = [("num_tris", C.c_int64), ("num_nodes", C.c_int64), ("max_depth", C.c_int32), ("reserved", C.c_int32),
                 ("scene_min", C.c_float * 3), ("scene_max", C.c_float * 3), ("box_pad", C.c_float),
@@ -93,6 +99,7 @@ SYMBOLS = {
     "lrc_peer_buffer_close": (_i32, [_vp, _vp]),
     "lrc_peer_buffer_destroy": (_i32, [_vp, _vp]),
     "lrc_set_gather": (_i32, [_vp, C.POINTER(Gather)]),
+    "lrc_set_gather_wire": (_i32, [_vp, C.POINTER(GatherWire)]),
     "lrc_gen_rays_single_axis": (_i32, [_vp, _vp, _i64, C.POINTER(SingleAxis), _vp, _vp]),
     "lrc_gen_rays_dual_axis": (_i32, [_vp, _vp, _i64, C.POINTER(DualAxis), C.POINTER(Noise), _vp, _vp, _vp]),
     "lrc_frame_statistics": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),

@@ -91,6 +91,11 @@ struct lrc_ctx {
         int64_t point_base = 0, frame_base = 0, capacity = 0;
         int64_t frame_capacity = 0;
     } gather;
+    lrc_gather_wire wire = {};         // compact wire format of the exchange (lrc_set_gather_wire); wire.enabled == 0: off
+    int64_t wire_scan = 0;             // scans issued since lrc_set_gather_wire: tags the progress words
+    cudaStream_t s_rebuild = nullptr;  // waits for the peers' progress words and rebuilds their points
+    cudaEvent_t rebuild_ev = nullptr;
+    int* d_wire_err = nullptr;         // set by the waiting kernel when a peer's progress word does not arrive in time
     int64_t opt_gather_chunks = 4;
     int64_t opt_gather_ramp = 1;        // first gather chunk = regular chunk / ramp
     int64_t opt_gather_taper = 1;       // last gather chunk = regular chunk / taper

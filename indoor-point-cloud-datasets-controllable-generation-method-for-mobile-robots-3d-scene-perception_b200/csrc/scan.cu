@@ -164,6 +164,7 @@ __global__ void k_gen_rays(RayGen g, int64_t n, float* __restrict__ rays, uint8_
 struct FrameMath {
     double max_range;          // < 0: no range filter, no incident angle (rays_intersect_mesh)
     double cx, cy, cz;         // frame centre for MODE_RAYS; scan modes read pose[:3,3]
+    int wire;                  // compact wire format: the 8-byte scratch slot of the angle carries the float32 hit distance t instead
 };
 
 // One ray's share of the frame arithmetic (see above): writes the scratch record of ray idx, returns whether it is kept.
@@ -191,10 +192,11 @@ __device__ __forceinline__ bool frame_epilogue(const RayGen& g, const FrameMath&
             const double ddx = __dsub_rn((double)o.x, cx), ddy = __dsub_rn((double)o.y, cy), ddz = __dsub_rn((double)o.z, cz);
             const double dist = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz)));
             keep = dist < fm.max_range;
-            if (inc_out) inc = __dmul_rn(acos(fabs(__ddiv_rn(ddz, dist))), 180.0 / PI_D);
+            if (inc_out && !fm.wire) inc = __dmul_rn(acos(fabs(__ddiv_rn(ddz, dist))), 180.0 / PI_D);
         }
         if (keep) o.w = __uint_as_float(id);
     }
+    if (fm.wire) inc = __longlong_as_double((long long)__float_as_uint(t));      // t after range noise: what p was built from
     if (CS) {      // evict-first: the scratch is read once by k_compact and should not push BVH lines out of L2
         __stcs(hp + idx, o);
         if (inc_out) __stcs(inc_out + idx, inc);
@@ -530,6 +532,8 @@ struct CompactParams {
     int64_t P;                 // frames of the whole call
     const uint32_t* labels;
     lrc_out out;
+    float* wire_t;             // compact wire format: hit distance and ray index of every kept point (this rank's region of its
+    uint32_t* wire_ray;        // own gather buffer, indexed like out.xyz); the scratch slot `inc` carries t then
 };
 
 // Launched with the block size k_trace used (one keep count per block of rays).
@@ -565,7 +569,10 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_compact(CompactParams q)
             q.out.xyz[3 * pos + 0] = h.x;
             q.out.xyz[3 * pos + 1] = h.y;
             q.out.xyz[3 * pos + 2] = h.z;
-            if (q.out.incident_deg) q.out.incident_deg[pos] = inc;
+            if (q.wire_t) {
+                q.wire_t[pos] = __uint_as_float((unsigned)__double_as_longlong(inc));
+                q.wire_ray[pos] = (uint32_t)r;
+            } else if (q.out.incident_deg) q.out.incident_deg[pos] = inc;
             if (q.out.prim_id) q.out.prim_id[pos] = id;
             if (q.out.label) q.out.label[pos] = q.labels ? __ldg(q.labels + id) : 0u;
             if (q.out.ray_idx) q.out.ray_idx[pos] = (uint32_t)r;
@@ -587,6 +594,10 @@ struct GatherTargets {
     uint32_t* label[LRC_MAX_GATHER];
     int64_t* frame_offset[LRC_MAX_GATHER];
     int64_t point_base, frame_base, capacity;
+    int wire, self;                        // compact wire format: t | label | ray index travel, xyz is rebuilt on arrival
+    float* wire_t[LRC_MAX_GATHER];
+    uint32_t* wire_ray[LRC_MAX_GATHER];
+    int64_t* ready[LRC_MAX_GATHER];
 };
 
 struct PushParams {
@@ -684,10 +695,22 @@ __global__ void __launch_bounds__(TMA_THREADS) k_push_tma(PushParams q, const __
     __shared__ __align__(8) unsigned long long bars[TMA_STAGES];
     const long long a = q.run[0], b = q.run[1];
     const long long gp = gt.point_base + a;
-    TmaStream st[2];
-    st[0].src = reinterpret_cast<const char*>(q.xyz + 3 * a); st[0].dst_off = 12 * gp; st[0].bytes = 12 * (b - a); st[0].kind = 0;
+    // streams of this chunk: xyz | label, or -- compact wire format -- t | label | ray index (xyz is rebuilt by the receiver)
+    TmaStream st[3];
+    int n_streams = 2;
+    if (gt.wire) {
+        n_streams = 3;
+        st[0].src = reinterpret_cast<const char*>(gt.wire_t[gt.self] + gp); st[0].dst_off = 4 * gp; st[0].bytes = 4 * (b - a); st[0].kind = 2;
+        st[2].src = reinterpret_cast<const char*>(gt.wire_ray[gt.self] + gp); st[2].dst_off = 4 * gp; st[2].bytes = 4 * (b - a); st[2].kind = 3;
+    } else {
+        st[0].src = reinterpret_cast<const char*>(q.xyz + 3 * a); st[0].dst_off = 12 * gp; st[0].bytes = 12 * (b - a); st[0].kind = 0;
+        st[2].src = nullptr; st[2].dst_off = 0; st[2].bytes = 0; st[2].kind = 0;
+    }
     st[1].src = reinterpret_cast<const char*>(q.label + a);   st[1].dst_off = 4 * gp;  st[1].bytes = q.label ? 4 * (b - a) : 0; st[1].kind = 1;
-    auto target_base = [&](int k, int kind) -> char* { return kind == 0 ? reinterpret_cast<char*>(gt.xyz[k]) : reinterpret_cast<char*>(gt.label[k]); };
+    auto target_base = [&](int k, int kind) -> char* {
+        return kind == 0 ? reinterpret_cast<char*>(gt.xyz[k]) : kind == 1 ? reinterpret_cast<char*>(gt.label[k])
+             : kind == 2 ? reinterpret_cast<char*>(gt.wire_t[k]) : reinterpret_cast<char*>(gt.wire_ray[k]);
+    };
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -698,7 +721,7 @@ __global__ void __launch_bounds__(TMA_THREADS) k_push_tma(PushParams q, const __
     __syncthreads();
 
     int64_t g0 = 0;       // tiles this block has pushed in earlier streams: stage and barrier parity continue from there
-    for (int sidx = 0; sidx < 2; ++sidx) {
+    for (int sidx = 0; sidx < n_streams; ++sidx) {
         const TmaStream& S = st[sidx];
         if (S.bytes <= 0) continue;
         // aligned middle [head, head + mid): source and destination are congruent modulo 16 when the rank's point base keeps
@@ -775,10 +798,91 @@ __global__ void __launch_bounds__(TMA_THREADS) k_push_tma(PushParams q, const __
             const int64_t f = i - (int64_t)k * q.nf;
             gt.frame_offset[k][gt.frame_base + q.f0 + f] = gt.point_base + q.frame_offset[q.f0 + f];
         }
-        if (q.last && threadIdx.x < gt.n) gt.frame_offset[threadIdx.x][gt.frame_base + q.P] = gt.point_base + b;
+        // the offset that closes this chunk (the next chunk writes the same value; the receiver of the compact wire format
+        // needs it to know where the chunk's points end)
+        if (threadIdx.x < gt.n) gt.frame_offset[threadIdx.x][gt.frame_base + q.f0 + q.nf] = gt.point_base + b;
     }
     // make the bulk stores of this block globally visible before the kernel (and with it the stream-ordered event) completes
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ---- compact wire format: progress words and the rebuild of the other ranks' points --------------------------------------
+// Producer side: after the bulk copies of a chunk have completed (k_push_tma ends with cp.async.bulk.wait_group 0 and the
+// kernel boundary orders everything before this launch), one store with release semantics at system scope tells every
+// target how many frames of this scan are complete: word = scan number << 32 | frames.
+__global__ void k_wire_flag(const __grid_constant__ GatherTargets gt, long long word)
+{
+    const int k = threadIdx.x;
+    if (k < gt.n) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(gt.ready[k] + gt.self), "l"(word) : "memory");
+    }
+}
+
+struct WireWait {
+    const int64_t* ready;                 // this rank's own progress words, one per rank
+    long long need[LRC_MAX_GATHER];       // value to wait for, per rank (0: nothing to wait for)
+    int n;
+};
+
+// Receiver side, one thread per peer: spin (acquire, system scope) until the peer's progress word has reached `need`.
+// ONE resident block, so waiting cannot starve the traversal.  A peer that never arrives (ranks out of step) ends the
+// wait after ~4 s and raises the error flag instead of hanging the GPU.
+__global__ void k_wire_wait(WireWait w, int* err)
+{
+    const int p = threadIdx.x;
+    if (p >= w.n || w.need[p] == 0) return;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w.ready + p) : "memory");
+        if (v >= w.need[p]) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 4000000000ull) { atomicExch(err, 1); break; }
+        __nanosleep(200);
+    }
+}
+
+struct RebuildParams {
+    float* xyz;                           // this rank's own gather arrays (all ranks' regions)
+    const float* wire_t;
+    const uint32_t* wire_ray;
+    const int64_t* frame_offset;
+    int n, self;
+    int64_t point_base[LRC_MAX_GATHER], frame_base[LRC_MAX_GATHER];
+    int64_t pose0[LRC_MAX_GATHER];        // first pose of every rank in g.poses
+    int64_t fa[LRC_MAX_GATHER], fb[LRC_MAX_GATHER];      // frames of every rank rebuilt by this launch
+    uint64_t pose_index_base;             // noise: global base (rank r's frame f draws stream base + pose0[r] + f)
+};
+
+// p = o + (d / |d|) * t for every point of the peers' frames [fa, fb): the ray is regenerated exactly as the producing rank
+// generated it (gen_ray: float64 tables / Philox, one rounding to float32), the point with frame_epilogue's operations.
+// blockIdx.y = rank; its points are found through its frame offsets (acquired by k_wire_wait, read around L1).
+template <int MODE>
+__global__ void __launch_bounds__(256) k_wire_rebuild(RayGen g, RebuildParams q)
+{
+    const int p = blockIdx.y;
+    if (p == q.self || q.fb[p] <= q.fa[p]) return;
+    const int64_t* off = q.frame_offset + q.frame_base[p];
+    const int64_t i0 = __ldcg(off + q.fa[p]), i1 = __ldcg(off + q.fb[p]);       // absolute point slots (carry the rank's base)
+    g.pose0 = q.pose0[p];
+    g.pose_index_base = q.pose_index_base;
+    for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t lo = q.fa[p], hi = q.fb[p];                 // largest f with off[f] <= i
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldcg(off + mid) <= i) lo = mid; else hi = mid;
+        }
+        const uint32_t r = __ldcg(q.wire_ray + i);
+        const float t = __ldcg(q.wire_t + i);
+        int64_t pose; int rr;
+        const Ray ray = gen_ray<MODE>(g, lo * (int64_t)g.N + (int64_t)r, pose, rr);
+        const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ray.dx, ray.dx), __fmul_rn(ray.dy, ray.dy)), __fmul_rn(ray.dz, ray.dz)));
+        q.xyz[3 * i + 0] = __fadd_rn(ray.ox, __fmul_rn(__fdiv_rn(ray.dx, nrm), t));
+        q.xyz[3 * i + 1] = __fadd_rn(ray.oy, __fmul_rn(__fdiv_rn(ray.dy, nrm), t));
+        q.xyz[3 * i + 2] = __fadd_rn(ray.oz, __fmul_rn(__fdiv_rn(ray.dz, nrm), t));
+    }
 }
 
 // ---- host-side launch plumbing -----------------------------------------------------------------------
@@ -1018,7 +1122,11 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
     const int TB = scan_block_threads(ctx, total);
     ctx->cur_block = TB;
     const int64_t max_blocks = (chunk_rays + TB - 1) / TB;
-    const bool want_inc = out->incident_deg != nullptr && max_range >= 0.0;
+    const bool wire = gather && ctx->wire.enabled && MODE != MODE_RAYS;
+    if (wire && out->incident_deg)
+        return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_gather_wire: the scan's lrc_out must not carry incident_deg (use lrc_incident_angles)");
+    if (wire && !out->label && ctx->T > 0) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_gather_wire: the scan's lrc_out needs a label array");
+    const bool want_inc = (out->incident_deg != nullptr && max_range >= 0.0) || wire;      // wire: the slot carries t
     const size_t hp_bytes = align_up(sizeof(float4) * (size_t)chunk_rays, 256);
     const size_t inc_bytes = want_inc ? align_up(sizeof(double) * (size_t)chunk_rays, 256) : 0;
     const size_t slot_bytes = hp_bytes + inc_bytes;
@@ -1056,9 +1164,30 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
     FrameMath fm;
     fm.max_range = max_range;
     fm.cx = h_center ? h_center[0] : 0.0; fm.cy = h_center ? h_center[1] : 0.0; fm.cz = h_center ? h_center[2] : 0.0;
+    fm.wire = wire ? 1 : 0;
     GatherTargets gt;
     memset(&gt, 0, sizeof gt);
+    long long wire_tag = 0;
+    if (wire) {
+        const lrc_gather_wire& W = ctx->wire;
+        if (W.rank_frames[W.self] != P)
+            return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_gather_wire: this scan's frame count differs from rank_frames[self]");
+        if (!ctx->s_rebuild) {
+            LRC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_rebuild, cudaStreamNonBlocking));
+            LRC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->rebuild_ev, cudaEventDisableTiming));
+            LRC_CUDA(ctx, cudaMalloc((void**)&ctx->d_wire_err, sizeof(int)));
+            LRC_CUDA(ctx, cudaMemset(ctx->d_wire_err, 0, sizeof(int)));
+        }
+        wire_tag = (long long)(++ctx->wire_scan) << 32;
+        // the rebuild stream reads the ray tables of this call and must not run ahead of it
+        LRC_CUDA(ctx, cudaEventRecord(ctx->rebuild_ev, stream));
+        LRC_CUDA(ctx, cudaStreamWaitEvent(ctx->s_rebuild, ctx->rebuild_ev, 0));
+    }
     if (gather) {
+        gt.wire = wire ? 1 : 0;
+        gt.self = wire ? ctx->wire.self : 0;
+        if (wire)
+            for (int k = 0; k < ctx->gather.n; ++k) { gt.wire_t[k] = ctx->wire.t[k]; gt.wire_ray[k] = ctx->wire.ray_idx[k]; gt.ready[k] = ctx->wire.ready[k]; }
         gt.n = ctx->gather.n;
         for (int k = 0; k < gt.n; ++k) { gt.xyz[k] = ctx->gather.xyz[k]; gt.label[k] = ctx->gather.label[k]; gt.frame_offset[k] = ctx->gather.frame_offset[k]; }
         gt.point_base = ctx->gather.point_base; gt.frame_base = ctx->gather.frame_base; gt.capacity = ctx->gather.capacity;
@@ -1091,7 +1220,9 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
         q.n = n; q.ray0 = f0 * N; q.N = N; q.total_rays = total; q.P = P;
         q.labels = ctx->T > 0 ? ctx->labels : nullptr;
         q.out = *out;
-        if (!want_inc) q.out.incident_deg = nullptr;
+        q.wire_t = wire ? ctx->wire.t[ctx->wire.self] + ctx->gather.point_base : nullptr;
+        q.wire_ray = wire ? ctx->wire.ray_idx[ctx->wire.self] + ctx->gather.point_base : nullptr;
+        if (!want_inc || wire) q.out.incident_deg = nullptr;
         if (ctx->T == 0) q.out.label = nullptr;
         if (gather && !q.out.label && ctx->T > 0) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_gather: the scan's lrc_out needs a label array");
         k_compact<<<(unsigned)nb, TB, 0, aux>>>(q);
@@ -1103,7 +1234,7 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
             PushParams pp;
             pp.xyz = out->xyz; pp.label = q.out.label; pp.frame_offset = out->frame_offset; pp.run = run + c;
             pp.f0 = f0; pp.nf = nf; pp.P = P; pp.last = last ? 1 : 0;
-            if (ctx->opt_push_mode == 1) {
+            if (ctx->opt_push_mode == 1 || wire) {
                 if (!ctx->push_tma_ready) {      // per context (= per device): the opt-in to 64 KB of dynamic shared memory
                     LRC_CUDA(ctx, cudaFuncSetAttribute(k_push_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_STAGES * TMA_TILE));
                     ctx->push_tma_ready = true;
@@ -1113,6 +1244,39 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
             } else {
                 k_push<<<dim3((unsigned)ctx->opt_push_blocks, (unsigned)gt.n), PUSH_THREADS, 0, aux>>>(pp, gt);
                 LRC_CHECK_LAUNCH(ctx, "k_push");
+            }
+            if (wire) {
+                // tell every target that frames [0, f0 + nf) of this scan are complete there ...
+                k_wire_flag<<<1, 32, 0, aux>>>(gt, wire_tag | (long long)(f0 + nf));
+                LRC_CHECK_LAUNCH(ctx, "k_wire_flag");
+                // ... and rebuild the points of the same frame range of every other rank as soon as THEIR words arrive
+                const lrc_gather_wire& W = ctx->wire;
+                WireWait ww;
+                memset(&ww, 0, sizeof ww);
+                ww.ready = W.ready[W.self];
+                ww.n = gt.n;
+                RebuildParams rp;
+                memset(&rp, 0, sizeof rp);
+                rp.xyz = ctx->gather.xyz[W.self]; rp.wire_t = W.t[W.self]; rp.wire_ray = W.ray_idx[W.self];
+                rp.frame_offset = ctx->gather.frame_offset[W.self];
+                rp.n = gt.n; rp.self = W.self;
+                rp.pose_index_base = g.pose_index_base - (uint64_t)W.rank_pose0[W.self];
+                bool any = false;
+                for (int p = 0; p < gt.n; ++p) {
+                    const int64_t Pp = W.rank_frames[p];
+                    rp.point_base[p] = W.rank_point_base[p]; rp.frame_base[p] = W.rank_frame_base[p]; rp.pose0[p] = W.rank_pose0[p];
+                    rp.fa[p] = f0 < Pp ? f0 : Pp;
+                    rp.fb[p] = last ? Pp : (f0 + nf < Pp ? f0 + nf : Pp);
+                    if (p != W.self && rp.fb[p] > rp.fa[p]) { ww.need[p] = wire_tag | (long long)rp.fb[p]; any = true; }
+                }
+                if (any) {
+                    k_wire_wait<<<1, 32, 0, ctx->s_rebuild>>>(ww, ctx->d_wire_err);
+                    LRC_CHECK_LAUNCH(ctx, "k_wire_wait");
+                    RayGen ga = g;
+                    ga.poses = W.all_poses;
+                    k_wire_rebuild<MODE><<<dim3((unsigned)ctx->num_sms, (unsigned)gt.n), 256, 0, ctx->s_rebuild>>>(ga, rp);
+                    LRC_CHECK_LAUNCH(ctx, "k_wire_rebuild");
+                }
             }
         }
         if (timing) { LRC_CUDA(ctx, cudaEventRecord(ctx->kt_events[4 * c + 3], aux)); ctx->kt_used = (size_t)(4 * (c + 1)); }
@@ -1125,6 +1289,10 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
         const int last_slot = (int)((n_chunks - 1) & 1);
         LRC_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->pipe_ev[last_slot], 0));
         if (n_chunks >= 2) LRC_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->pipe_ev[last_slot ^ 1], 0));
+    }
+    if (wire) {      // the caller's stream owns the whole gathered cloud, rebuilt points included
+        LRC_CUDA(ctx, cudaEventRecord(ctx->rebuild_ev, ctx->s_rebuild));
+        LRC_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->rebuild_ev, 0));
     }
     LRC_CUDA(ctx, cudaEventRecord(ctx->scratch_event, stream));
     if (out->incident_deg && !want_inc)   // rays_intersect_mesh flavour: no angles are defined; keep the buffer deterministic
@@ -1253,6 +1421,7 @@ extern "C" void lrc_destroy(lrc_ctx* ctx)
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->scratch_event) cudaEventDestroy(ctx->scratch_event);
     if (ctx->tables_event) cudaEventDestroy(ctx->tables_event);
+    if (ctx->s_rebuild) { cudaStreamDestroy(ctx->s_rebuild); cudaEventDestroy(ctx->rebuild_ev); cudaFree(ctx->d_wire_err); }
     for (cudaEvent_t e : ctx->kt_events) cudaEventDestroy(e);
     if (ctx->s_aux) { cudaStreamDestroy(ctx->s_aux); for (int k = 0; k < 4; ++k) cudaEventDestroy(ctx->pipe_ev[k]); }
     for (size_t i = 0; i < ctx->n_events; ++i) cudaEventDestroy(ctx->events[i]);
@@ -1303,6 +1472,16 @@ extern "C" int lrc_get_stat(lrc_ctx* ctx, const char* key, int64_t* h_value)
     if (!strcmp(key, "rays_per_thread")) { *h_value = ctx->opt_rays_per_thread; return LRC_OK; }
     if (!strcmp(key, "persistent")) { *h_value = ctx->opt_persistent; return LRC_OK; }
     if (!strcmp(key, "num_sms")) { *h_value = ctx->num_sms; return LRC_OK; }
+    if (!strcmp(key, "wire_error")) {      // 1: a peer's progress word did not arrive in time during some scan (synchronises the device)
+        int e = 0;
+        if (ctx->d_wire_err) {
+            LRC_CUDA(ctx, cudaSetDevice(ctx->device));
+            LRC_CUDA(ctx, cudaDeviceSynchronize());
+            LRC_CUDA(ctx, cudaMemcpy(&e, ctx->d_wire_err, sizeof e, cudaMemcpyDeviceToHost));
+        }
+        *h_value = e;
+        return LRC_OK;
+    }
     if (!strcmp(key, "nn_generation")) { *h_value = ctx->nn_generation; return LRC_OK; }
     if (!strcmp(key, "collision_generation")) { *h_value = ctx->ci_generation; return LRC_OK; }
     if (!strcmp(key, "mesh_generation")) { *h_value = ctx->mesh_generation; return LRC_OK; }
@@ -1769,9 +1948,31 @@ extern "C" int lrc_peer_buffer_destroy(lrc_ctx* ctx, void* d_ptr)
     return LRC_OK;
 }
 
+extern "C" int lrc_set_gather_wire(lrc_ctx* ctx, const lrc_gather_wire* w)
+{
+    if (!ctx) return lrc_fail(nullptr, LRC_ERR_INVALID, "lrc_set_gather_wire: ctx is NULL");
+    memset(&ctx->wire, 0, sizeof ctx->wire);
+    ctx->wire_scan = 0;
+    if (!w || !w->enabled) return LRC_OK;
+    if (ctx->gather.n <= 0) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_gather_wire: call lrc_set_gather first");
+    if (w->self < 0 || w->self >= ctx->gather.n || !w->all_poses) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_gather_wire: bad self / all_poses");
+    for (int k = 0; k < ctx->gather.n; ++k) {
+        if (!w->t[k] || !w->ray_idx[k] || !w->ready[k]) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_gather_wire: every target needs t, ray_idx and ready");
+        if (w->rank_frames[k] < 0 || w->rank_pose0[k] < 0 || w->rank_point_base[k] < 0 || w->rank_frame_base[k] < 0)
+            return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_gather_wire: negative rank table entry");
+        if (w->rank_frames[k] >= ((int64_t)1 << 31)) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_gather_wire: too many frames");
+    }
+    if (w->rank_point_base[w->self] != ctx->gather.point_base || w->rank_frame_base[w->self] != ctx->gather.frame_base)
+        return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_gather_wire: rank tables disagree with lrc_set_gather for this rank");
+    ctx->wire = *w;
+    return LRC_OK;
+}
+
 extern "C" int lrc_set_gather(lrc_ctx* ctx, const lrc_gather* h_targets)
 {
     if (!ctx) return lrc_fail(nullptr, LRC_ERR_INVALID, "lrc_set_gather: ctx is NULL");
+    memset(&ctx->wire, 0, sizeof ctx->wire);          // the compact wire format belongs to one set of targets
+    ctx->wire_scan = 0;
     if (!h_targets || h_targets->n_targets == 0) { memset(&ctx->gather, 0, sizeof ctx->gather); return LRC_OK; }
     if (h_targets->n_targets < 0 || h_targets->n_targets > LRC_MAX_GATHER) return lrc_fail(ctx, LRC_ERR_INVALID, "lrc_set_gather: n_targets out of range");
     for (int k = 0; k < h_targets->n_targets; ++k)

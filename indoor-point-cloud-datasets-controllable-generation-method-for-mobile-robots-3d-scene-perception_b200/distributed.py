@@ -253,7 +253,12 @@ class PeerGather:
         w = self.world
         self.o_lab = (w * self.cap * 12 + 255) // 256 * 256
         self.o_off = (self.o_lab + w * self.cap * 4 + 255) // 256 * 256
-        self.nbytes = (self.o_off + w * (self.pmax + 1) * 8 + 255) // 256 * 256
+        # compact wire format (enable(wire=True)): hit distance and ray index per point, one progress word per rank
+        self.o_t = (self.o_off + w * (self.pmax + 1) * 8 + 255) // 256 * 256
+        self.o_ray = (self.o_t + w * self.cap * 4 + 255) // 256 * 256
+        self.o_ready = (self.o_ray + w * self.cap * 4 + 255) // 256 * 256
+        self.nbytes = (self.o_ready + w * 8 + 255) // 256 * 256
+        self.wire = False
         lib = ctx._lib
         ptr, handle = C.c_void_p(), nat.IpcHandle()
         with torch.cuda.device(ctx.device):
@@ -291,32 +296,74 @@ class PeerGather:
         if w > 1:
             dist.barrier(group=group)
 
-    def local_out(self, frames: Optional[int] = None) -> Dict[str, torch.Tensor]:
+    def local_out(self, frames: Optional[int] = None, incident: Optional[bool] = None) -> Dict[str, torch.Tensor]:
         """Output buffers for ``Context.scan_enqueue`` that ARE this rank's region of its own gather buffer: the compaction
         then writes the local cloud straight to its final place and the exchange kernel skips the copy to itself (one
         target and one pass over the local cloud less per step).  ``off`` is a private (P+1,) array -- the gathered
         offsets carry each rank's point base and are written by the exchange kernel."""
         xyz, lab, _ = self.views()
         nf = self.pmax if frames is None else int(frames)
-        if getattr(self, "_local_inc", None) is None:
+        want_inc = (not self.wire) if incident is None else bool(incident)      # the compact wire format produces no local angles
+        if want_inc and getattr(self, "_local_inc", None) is None:
             self._local_inc = torch.empty(self.cap, dtype=torch.float64, device=self.ctx.device)
-        return {"xyz": xyz[self.rank], "incident": self._local_inc, "prim": None, "label": lab[self.rank], "ray": None,
+        return {"xyz": xyz[self.rank], "incident": self._local_inc if want_inc else None, "prim": None, "label": lab[self.rank], "ray": None,
                 "off": torch.zeros(nf + 1, dtype=torch.int64, device=self.ctx.device)}
 
-    def enable(self):
+    def enable(self, wire: bool = False, poses_all=None, frames_per_rank: Optional[List[int]] = None):
+        """Switch the exchange on for the scans that follow.  ``wire=True`` selects the compact wire format
+        (``lrc_set_gather_wire``): t | label | ray index travel (12 B per point instead of 16) and every rank rebuilds the
+        other ranks' points on arrival from ``poses_all`` ((P_total,4,4), rank-major, rank r owning ``frames_per_rank[r]``
+        of them) -- bit-identical, 25 % less NVLink traffic.  Collective when ``wire`` is set: every rank must call it, then
+        issue the same sequence of scans, each of exactly its ``frames_per_rank`` frames, without an ``incident`` output
+        (``local_out()`` leaves it out; ``incident()`` recomputes the angles of the whole cloud)."""
         import ctypes as C
         from . import _native as nat
-        nat.check(self.ctx._h, self.ctx._lib.lrc_set_gather(self.ctx._h, C.byref(self._g)))
+        ctx = self.ctx
+        nat.check(ctx._h, ctx._lib.lrc_set_gather(ctx._h, C.byref(self._g)))
+        self.wire = bool(wire)
+        if not wire:
+            return
+        w = self.world
+        nfs = [self.pmax] * w if frames_per_rank is None else [int(x) for x in frames_per_rank]
+        poses = np.ascontiguousarray(poses_all, dtype=np.float64).reshape(-1, 16)
+        if len(poses) != sum(nfs) or max(nfs) > self.pmax:
+            raise ValueError("poses_all must hold frames_per_rank[r] <= frames_per_rank of the constructor poses for every rank")
+        with torch.cuda.device(ctx.device):
+            self._wire_poses = torch.from_numpy(poses).to(ctx.device)
+            # progress words of earlier scans must not satisfy the waits of the new ones
+            torch.cuda.synchronize()
+            if w > 1:
+                dist.barrier(group=self.group)
+            self.buffer[self.o_ready: self.o_ready + w * 8].zero_()
+            torch.cuda.synchronize()
+            if w > 1:
+                dist.barrier(group=self.group)
+        gw = nat.GatherWire()
+        gw.enabled, gw.self_index = 1, self.rank
+        p0 = 0
+        for r in range(w):
+            gw.t[r] = self.ptrs[r] + self.o_t
+            gw.ray_idx[r] = self.ptrs[r] + self.o_ray
+            gw.ready[r] = self.ptrs[r] + self.o_ready
+            gw.rank_pose0[r], gw.rank_frames[r] = p0, nfs[r]
+            gw.rank_point_base[r], gw.rank_frame_base[r] = r * self.cap, r * (self.pmax + 1)
+            p0 += nfs[r]
+        gw.all_poses = self._wire_poses.data_ptr()
+        self._gw = gw
+        nat.check(ctx._h, ctx._lib.lrc_set_gather_wire(ctx._h, C.byref(gw)))
 
     def disable(self):
         from . import _native as nat
         nat.check(self.ctx._h, self.ctx._lib.lrc_set_gather(self.ctx._h, None))
+        self.wire = False
 
     def synchronize(self):
         """Make every rank's stores visible here: local stream sync, then a barrier across ranks."""
         torch.cuda.synchronize(self.ctx.device)
         if self.world > 1:
             dist.barrier(group=self.group)
+        if self.wire and self.ctx.stat("wire_error"):
+            raise RuntimeError("PeerGather: a peer's progress word did not arrive in time -- the ranks did not issue the same scans")
 
     def views(self):
         w = self.world

@@ -93,6 +93,29 @@ def main():
     assert np.array_equal(local["points"], ref["points"][a:b]) and np.array_equal(local["incident"], ref["incident"][a:b])
     pg.close()
     dist.barrier()
+    # compact wire format: t | label | ray index travel, every rank rebuilds the other ranks' points on arrival
+    # (noisy dual-axis sensor and a single-axis sensor whose frame is not a multiple of the block size)
+    nfs = [len(lrc.shard_range(len(poses12), r, world)) for r in range(world)]
+    for sensor, nz_all in ((intr, noise), (lrc.Indoor8LineLidarIntrinsics(max_range=5.0, horizontal_res=999), None)):
+        refw = engine.simulate(poses12, sensor, mesh, noise=nz_all).numpy()
+        n_ray = lrc.rays_per_frame(sensor)
+        pgw = PeerGather(engine.ctx, cap_per_rank=max(nfs) * n_ray, frames_per_rank=max(nfs))
+        pgw.enable(wire=True, poses_all=poses12, frames_per_rank=nfs)
+        ln = None if nz_all is None else lrc.NoiseConfig(nz_all.angle_noise_std, nz_all.dropout_probability, 0.0, nz_all.seed, sl.start)
+        for chunks in (3, 1, 2):
+            engine.ctx.set_option("gather_chunks", chunks)
+            pgw.buffer[: pgw.o_lab].zero_()                       # wipe every rank's xyz: what is compared below was rebuilt in this pass
+            torch.cuda.synchronize()
+            dist.barrier()
+            engine.ctx.scan(poses12[sl.start:sl.stop], sensor, ln, bufs=pgw.local_out(sl.stop - sl.start))
+            pgw.synchronize()
+            got = pgw.assemble_numpy(frames_per_rank=nfs, poses_all=poses12)
+            for k in ("frame_offset", "points", "label", "incident"):
+                assert np.array_equal(got[k], refw[k]), ("wire", type(sensor).__name__, chunks, k)
+            dist.barrier()
+        pgw.close()
+        dist.barrier()
+    engine.ctx.set_option("gather_chunks", 4)
     if dist.get_rank() == 0:
         print("MGPU_OK world=%d" % dist.get_world_size())
     dist.destroy_process_group()

@@ -132,6 +132,7 @@ def test_two_planners_do_not_share_a_collision_index(lrc):
 def test_gathered_record_is_complete_and_regions_are_guarded(lrc):
     """world = 1 form of the exchange: the gather buffer receives xyz + label + offsets; the incident angles recomputed
     on arrival equal the scan's own bit for bit; a scan with more frames than the region holds is refused."""
+    import torch
     from lrc_b200.distributed import PeerGather
     engine = lrc.RaycastEngineGPU()
     ctx = engine.ctx
@@ -162,6 +163,20 @@ def test_gathered_record_is_complete_and_regions_are_guarded(lrc):
         for k in ("frame_offset", "points", "label", "incident"):
             assert np.array_equal(got[k], ref[k]), ("local_out", k)
         assert np.array_equal(direct["points"], ref["points"]) and np.array_equal(direct["incident"], ref["incident"])
+        # compact wire format with a single rank: nothing to rebuild, the local cloud and its t | ray index arrays are written
+        pg.enable(wire=True, poses_all=poses)
+        pg.buffer.zero_()
+        ctx.scan(poses, intr, noise, bufs=pg.local_out(5))
+        pg.synchronize()
+        got = pg.assemble_numpy(poses_all=poses)
+        for k in ("frame_offset", "points", "label", "incident"):
+            assert np.array_equal(got[k], ref[k]), ("wire", k)
+        m = int(ref["frame_offset"][-1])
+        ray = pg.buffer[pg.o_ray: pg.o_ray + 4 * m].view(torch.int32).cpu().numpy().view(np.uint32)
+        assert np.array_equal(ray, ref["ray_idx"])
+        with pytest.raises(RuntimeError, match="incident_deg"):
+            ctx.scan(poses, intr, noise, bufs=pg.local_out(5, incident=True))
+        pg.enable()
         more = lrc.poses_from_waypoints([lrc.Waypoint(1.5 + 0.4 * k, 3.2, 1.0, 0.0) for k in range(6)])
         with pytest.raises(RuntimeError, match="frame_capacity"):
             engine.simulate(more[:6], lrc.Indoor8LineLidarIntrinsics(max_range=5.0))
