@@ -334,6 +334,7 @@ class Leg:
         self.poses_d = torch.from_numpy(np.ascontiguousarray(self.poses.reshape(-1, 16))).to(dev)
         self.bufs, _ = ctx._alloc_out(max(1, self.P * self.n_frame), self.P)
         self.peer = None
+        self.wire = False
 
     def enable_gather(self, args):
         from lrc_b200.distributed import PeerGather
@@ -349,9 +350,18 @@ class Leg:
             self.ctx.set_option("gather_taper", args.gather_taper)
         if args.push_mode is not None:
             self.ctx.set_option("push_mode", args.push_mode)
-        self.peer.enable()
-        if not args.gather_copy_self:
-            self.bufs = self.peer.local_out(self.P)        # compact straight into this rank's region of its own gather buffer
+        # compact wire format (t | label | ray index, 12 B per point; points rebuilt on arrival), "--wire 1".  Measured equal to
+        # xyz | label at 8 GPUs (3.05 vs 3.07 ms per step: what the link saves the rebuild kernels spend) and slower below, so off
+        # by default (profiles/r02h_scaling.md)
+        self.wire = bool(args.wire == 1)
+        if self.wire:
+            nfs = [len(self.lrc.shard_range(len(self.poses_all), r, self.world)) for r in range(self.world)]
+            self.peer.enable(wire=True, poses_all=self.poses_all, frames_per_rank=nfs)
+            self.bufs = self.peer.local_out(self.P)
+        else:
+            self.peer.enable()
+            if not args.gather_copy_self:
+                self.bufs = self.peer.local_out(self.P)    # compact straight into this rank's region of its own gather buffer
 
     def step(self):
         self.ctx.scan_enqueue(self.poses_d, self.intr, self.noise, self.bufs)
@@ -605,10 +615,15 @@ def run_ours(args):
     if leg.peer is not None:
         gather_check = leg.verify_gather(dist)
         pts = leg.total_pts
-        exchange = {"bytes_out_per_gpu_per_step": int(pts * 16 * (world - 1)), "bytes_in_per_gpu_per_step": int(pts * 16 * (world - 1)),
-                    "record": "xyz 12 B + label 4 B per point + frame offsets; incident angles are recomputed on arrival (lrc_incident_angles)",
-                    "nvlink_ingest_gbs_over_step": round(pts * 16 * (world - 1) / (ms_per_step * 1e-3) / 1e9, 1),
-                    "nvlink_ingest_gbs_over_exchange_kernels": round(pts * 16 * (world - 1) / max(1e-9, split["after_trace_ms_per_step"] * 1e-3) / 1e9, 1)}
+        bpp = 12 if leg.wire else 16
+        exchange = {"bytes_out_per_gpu_per_step": int(pts * bpp * (world - 1)), "bytes_in_per_gpu_per_step": int(pts * bpp * (world - 1)),
+                    "bytes_per_point_on_the_wire": bpp,
+                    "record": ("t 4 B + label 4 B + ray index 4 B per point + frame offsets; every rank rebuilds the other ranks' xyz on arrival "
+                               "(same ray generation and float32 point arithmetic as the scan, bit-identical) and recomputes incident angles on demand"
+                               if leg.wire else
+                               "xyz 12 B + label 4 B per point + frame offsets; incident angles are recomputed on arrival (lrc_incident_angles)"),
+                    "nvlink_ingest_gbs_over_step": round(pts * bpp * (world - 1) / (ms_per_step * 1e-3) / 1e9, 1),
+                    "nvlink_ingest_gbs_over_exchange_kernels": round(pts * bpp * (world - 1) / max(1e-9, split["after_trace_ms_per_step"] * 1e-3) / 1e9, 1)}
 
     # ---- end to end through the reference-facing API with host buffers ----
     pinned_pose = torch.from_numpy(np.ascontiguousarray(leg.poses.reshape(-1, 16))).pin_memory()
@@ -729,6 +744,7 @@ def run_ours(args):
                 extras[name] = extra_leg(lrc, torch, dist, ctx, dev, args, name, rank, world, flush, mesh_cache)
 
     line = None
+    leg_wire = leg.wire
     if rank == 0:
         cfg = workload_config(args, w, len(tris), n_frame, world)
         line = {
@@ -739,8 +755,9 @@ def run_ours(args):
             "run": {"numa_node_rank0": numa, "l2_persist_pct": int(args.l2_persist) if args.l2_persist is not None else ctx.default_l2_persist(),
                     "build_tag": tag, "host_threads": host_threads(),
                     "collective": ("none" if world == 1 else
-                                   f"all-gather over NVLink peer memory: each compacted pose chunk's xyz|label|frame_offset is pushed to the other {world - 1} ranks by an "
-                                   f"exchange kernel (TMA bulk copies global -> shared -> peer; --push-mode 0: 16 B vector stores) while the next chunk is traversed; "
+                                   f"all-gather over NVLink peer memory: each compacted pose chunk's {'t|label|ray index' if leg_wire else 'xyz|label'}|frame_offset is pushed to the other {world - 1} ranks by an "
+                                   f"exchange kernel (TMA bulk copies global -> shared -> peer; --push-mode 0: 16 B vector stores) while the next chunk is traversed"
+                                   f"{'; the other ranks rebuild xyz on arrival (release/acquire progress words, own stream), still' if leg_wire else ';'} "
                                    f"{args.gather_chunks} chunks, inside the step" if args.gather == "p2p" else
                                    f"NCCL all-gather of xyz|label|frame_offset blocks, {args.gather_chunks} chunks, overlapped with traversal, inside the step"),
                     "process_group": "none" if world == 1 else "nccl (barrier, all_reduce of timings and of the gather check)"},
@@ -795,6 +812,7 @@ def main():
     ap.add_argument("--gather-copy-self", action="store_true", help="N>1: compact into private buffers and let the exchange kernel copy to the own gather buffer too (round-1 behaviour)")
     ap.add_argument("--gather-ramp", type=int, default=None, help="N>1: first chunk = regular chunk / ramp")
     ap.add_argument("--gather-taper", type=int, default=3, help="N>1: last chunk = regular chunk / taper (its exchange is not hidden behind a traversal)")
+    ap.add_argument("--wire", type=int, default=0, help="N>1: compact wire format of the exchange (1 on; default off)")
     ap.add_argument("--push-mode", type=int, default=None, help="N>1: exchange kernel, 0 = vector loads / stores, 1 = TMA bulk copies")
     ap.add_argument("--push-blocks", type=int, default=None, help="N>1: blocks per target of the exchange kernel")
     ap.add_argument("--e2e-chunk", type=int, default=None, help="poses per chunk of the pipelined e2e path")

@@ -860,28 +860,26 @@ struct RebuildParams {
 // generated it (gen_ray: float64 tables / Philox, one rounding to float32), the point with frame_epilogue's operations.
 // blockIdx.y = rank; its points are found through its frame offsets (acquired by k_wire_wait, read around L1).
 template <int MODE>
-__global__ void __launch_bounds__(256) k_wire_rebuild(RayGen g, RebuildParams q)
+__global__ void __launch_bounds__(256) k_wire_rebuild(RayGen g, RebuildParams q, int sub_blocks)
 {
     const int p = blockIdx.y;
-    if (p == q.self || q.fb[p] <= q.fa[p]) return;
+    if (p == q.self) return;
+    // one frame per group of `sub_blocks` blocks: the pose is loop-invariant, no search for the frame of a point
+    const int64_t f = q.fa[p] + (int64_t)(blockIdx.x / sub_blocks);
+    if (f >= q.fb[p]) return;
+    const int sub = blockIdx.x % sub_blocks;
     const int64_t* off = q.frame_offset + q.frame_base[p];
-    const int64_t i0 = __ldcg(off + q.fa[p]), i1 = __ldcg(off + q.fb[p]);       // absolute point slots (carry the rank's base)
+    const int64_t i0 = __ldcg(off + f), i1 = __ldcg(off + f + 1);       // absolute point slots (carry the rank's base)
     g.pose0 = q.pose0[p];
     g.pose_index_base = q.pose_index_base;
-    for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t lo = q.fa[p], hi = q.fb[p];                 // largest f with off[f] <= i
-        while (hi - lo > 1) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (__ldcg(off + mid) <= i) lo = mid; else hi = mid;
-        }
-        const uint32_t r = __ldcg(q.wire_ray + i);
+    for (int64_t i = i0 + (int64_t)sub * blockDim.x + threadIdx.x; i < i1; i += (int64_t)sub_blocks * blockDim.x) {
+        const int r = (int)__ldcg(q.wire_ray + i);
         const float t = __ldcg(q.wire_t + i);
-        int64_t pose; int rr;
-        const Ray ray = gen_ray<MODE>(g, lo * (int64_t)g.N + (int64_t)r, pose, rr);
+        const Ray ray = MODE == MODE_SINGLE ? gen_single(g, f, r) : gen_dual(g, f, r);
         const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ray.dx, ray.dx), __fmul_rn(ray.dy, ray.dy)), __fmul_rn(ray.dz, ray.dz)));
-        q.xyz[3 * i + 0] = __fadd_rn(ray.ox, __fmul_rn(__fdiv_rn(ray.dx, nrm), t));
-        q.xyz[3 * i + 1] = __fadd_rn(ray.oy, __fmul_rn(__fdiv_rn(ray.dy, nrm), t));
-        q.xyz[3 * i + 2] = __fadd_rn(ray.oz, __fmul_rn(__fdiv_rn(ray.dz, nrm), t));
+        __stcs(q.xyz + 3 * i + 0, __fadd_rn(ray.ox, __fmul_rn(__fdiv_rn(ray.dx, nrm), t)));
+        __stcs(q.xyz + 3 * i + 1, __fadd_rn(ray.oy, __fmul_rn(__fdiv_rn(ray.dy, nrm), t)));
+        __stcs(q.xyz + 3 * i + 2, __fadd_rn(ray.oz, __fmul_rn(__fdiv_rn(ray.dz, nrm), t)));
     }
 }
 
@@ -1274,7 +1272,12 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
                     LRC_CHECK_LAUNCH(ctx, "k_wire_wait");
                     RayGen ga = g;
                     ga.poses = W.all_poses;
-                    k_wire_rebuild<MODE><<<dim3((unsigned)ctx->num_sms, (unsigned)gt.n), 256, 0, ctx->s_rebuild>>>(ga, rp);
+                    int64_t max_frames = 0;
+                    for (int p = 0; p < gt.n; ++p)
+                        if (p != W.self && rp.fb[p] - rp.fa[p] > max_frames) max_frames = rp.fb[p] - rp.fa[p];
+                    int sub_blocks = (int)((N + 256 * 8 - 1) / (256 * 8));        // ~8 points per thread
+                    if (sub_blocks < 1) sub_blocks = 1;
+                    k_wire_rebuild<MODE><<<dim3((unsigned)(max_frames * sub_blocks), (unsigned)gt.n), 256, 0, ctx->s_rebuild>>>(ga, rp, sub_blocks);
                     LRC_CHECK_LAUNCH(ctx, "k_wire_rebuild");
                 }
             }
