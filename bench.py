@@ -350,6 +350,8 @@ class Leg:
             self.ctx.set_option("gather_taper", args.gather_taper)
         if args.push_mode is not None:
             self.ctx.set_option("push_mode", args.push_mode)
+        if args.push_tile:
+            self.ctx.set_option("push_tile", args.push_tile)
         # compact wire format (t | label | ray index, 12 B per point; points rebuilt on arrival), "--wire 1".  Measured equal to
         # xyz | label at 8 GPUs (3.05 vs 3.07 ms per step: what the link saves the rebuild kernels spend) and slower below, so off
         # by default (profiles/r02h_scaling.md)
@@ -813,6 +815,7 @@ def main():
     ap.add_argument("--gather-ramp", type=int, default=None, help="N>1: first chunk = regular chunk / ramp")
     ap.add_argument("--gather-taper", type=int, default=3, help="N>1: last chunk = regular chunk / taper (its exchange is not hidden behind a traversal)")
     ap.add_argument("--wire", type=int, default=0, help="N>1: compact wire format of the exchange (1 on; default off)")
+    ap.add_argument("--push-tile", type=int, default=None, help="N>1: bytes per stage of the TMA exchange kernel (2048 ... 16384)")
     ap.add_argument("--push-mode", type=int, default=None, help="N>1: exchange kernel, 0 = vector loads / stores, 1 = TMA bulk copies")
     ap.add_argument("--push-blocks", type=int, default=None, help="N>1: blocks per target of the exchange kernel")
     ap.add_argument("--e2e-chunk", type=int, default=None, help="poses per chunk of the pipelined e2e path")

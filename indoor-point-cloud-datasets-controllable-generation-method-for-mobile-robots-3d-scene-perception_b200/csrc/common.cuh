@@ -102,6 +102,7 @@ struct lrc_ctx {
     int64_t opt_scan_chunks = 1;        // pose chunks of a scan WITHOUT gather targets (compaction of chunk c behind the traversal of c+1)
     int64_t opt_scan_taper = 1;         // ... last chunk = regular chunk / taper
     int64_t opt_push_blocks = 64;       // blocks in total of k_push_tma (push_mode 1) / blocks per target of k_push (push_mode 0; 16 measured best there)
+    int64_t opt_push_tile = 16384;      // bytes per stage of k_push_tma (4 stages of shared memory per block)
     bool push_tma_ready = false;        // cudaFuncSetAttribute(k_push_tma, max dynamic shared memory) done on this device
     int64_t opt_push_mode = 1;          // exchange kernel: 1 = k_push_tma (TMA bulk copies, default), 0 = k_push (vector loads / stores)
 

@@ -664,7 +664,7 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_push(PushParams q, const __gri
 // peer memory over NVLink included) -- the tile is read from HBM once instead of once per target, no data touches a
 // register, and a handful of blocks keeps megabytes in flight.  Streams: the chunk's xyz bytes and label bytes; their
 // 16-byte-aligned middle goes through TMA, the (at most 15-byte) head and tail and the frame offsets through plain stores.
-constexpr int TMA_TILE = 16384;
+constexpr int TMA_TILE_MAX = 16384;      // bytes per stage (option "push_tile": 2048 ... 16384; shared memory per block = 4 stages)
 constexpr int TMA_STAGES = 4;
 constexpr int TMA_THREADS = 64;
 
@@ -689,7 +689,7 @@ struct TmaStream {
     int kind;               // 0 = xyz, 1 = label
 };
 
-__global__ void __launch_bounds__(TMA_THREADS) k_push_tma(PushParams q, const __grid_constant__ GatherTargets gt)
+__global__ void __launch_bounds__(TMA_THREADS) k_push_tma(PushParams q, const __grid_constant__ GatherTargets gt, int tile)
 {
     extern __shared__ __align__(128) unsigned char tma_smem[];
     __shared__ __align__(8) unsigned long long bars[TMA_STAGES];
@@ -733,14 +733,14 @@ __global__ void __launch_bounds__(TMA_THREADS) k_push_tma(PushParams q, const __
             congruent = congruent && ((((uintptr_t)(target_base(k, S.kind) + S.dst_off)) & 15u) == (((uintptr_t)S.src) & 15u));
         const int64_t mid = congruent ? ((S.bytes - head) & ~(int64_t)15) : 0;
         if (!congruent) head = 0;
-        const int64_t n_tiles = (mid + TMA_TILE - 1) / TMA_TILE;
+        const int64_t n_tiles = (mid + tile - 1) / tile;
         // tiles of this block: blockIdx.x, blockIdx.x + gridDim.x, ...
         const int64_t mine = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
         if (threadIdx.x == 0 && mine > 0) {
             auto tile_bytes = [&](int64_t i) -> uint32_t {
                 const int64_t t = blockIdx.x + i * gridDim.x;
-                const int64_t left = mid - t * TMA_TILE;
-                return (uint32_t)(left < TMA_TILE ? left : TMA_TILE);
+                const int64_t left = mid - t * tile;
+                return (uint32_t)(left < tile ? left : tile);
             };
             auto issue_load = [&](int64_t i) {
                 const int stage = (int)((g0 + i) % TMA_STAGES);
@@ -749,7 +749,7 @@ __global__ void __launch_bounds__(TMA_THREADS) k_push_tma(PushParams q, const __
                 const uint32_t bar = smem_u32(&bars[stage]);
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(nb) : "memory");
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             :: "r"(smem_u32(tma_smem + stage * TMA_TILE)), "l"(S.src + head + t * TMA_TILE), "r"(nb), "r"(bar) : "memory");
+                             :: "r"(smem_u32(tma_smem + stage * tile)), "l"(S.src + head + t * tile), "r"(nb), "r"(bar) : "memory");
             };
             static_assert(TMA_STAGES >= 3, "the pipeline keeps TMA_STAGES - 2 loads ahead");
             const int ahead = TMA_STAGES - 2;
@@ -766,10 +766,10 @@ __global__ void __launch_bounds__(TMA_THREADS) k_push_tma(PushParams q, const __
                 const int64_t t = blockIdx.x + i * gridDim.x;
                 const uint32_t nb = tile_bytes(i);
                 for (int k = 0; k < gt.n; ++k) {
-                    char* dst = target_base(k, S.kind) + S.dst_off + head + t * TMA_TILE;
-                    if (dst == S.src + head + t * TMA_TILE) continue;       // this rank's own region already holds the data
+                    char* dst = target_base(k, S.kind) + S.dst_off + head + t * tile;
+                    if (dst == S.src + head + t * tile) continue;       // this rank's own region already holds the data
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                 :: "l"(dst), "r"(smem_u32(tma_smem + stage * TMA_TILE)), "r"(nb) : "memory");
+                                 :: "l"(dst), "r"(smem_u32(tma_smem + stage * tile)), "r"(nb) : "memory");
                 }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
@@ -1234,10 +1234,10 @@ int run_scan(lrc_ctx* ctx, RayGen g, int64_t P, int64_t N, const double* h_cente
             pp.f0 = f0; pp.nf = nf; pp.P = P; pp.last = last ? 1 : 0;
             if (ctx->opt_push_mode == 1 || wire) {
                 if (!ctx->push_tma_ready) {      // per context (= per device): the opt-in to 64 KB of dynamic shared memory
-                    LRC_CUDA(ctx, cudaFuncSetAttribute(k_push_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_STAGES * TMA_TILE));
+                    LRC_CUDA(ctx, cudaFuncSetAttribute(k_push_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_STAGES * TMA_TILE_MAX));
                     ctx->push_tma_ready = true;
                 }
-                k_push_tma<<<(unsigned)ctx->opt_push_blocks, TMA_THREADS, TMA_STAGES * TMA_TILE, aux>>>(pp, gt);
+                k_push_tma<<<(unsigned)ctx->opt_push_blocks, TMA_THREADS, TMA_STAGES * (size_t)ctx->opt_push_tile, aux>>>(pp, gt, (int)ctx->opt_push_tile);
                 LRC_CHECK_LAUNCH(ctx, "k_push_tma");
             } else {
                 k_push<<<dim3((unsigned)ctx->opt_push_blocks, (unsigned)gt.n), PUSH_THREADS, 0, aux>>>(pp, gt);
@@ -1565,6 +1565,11 @@ extern "C" int lrc_set_option(lrc_ctx* ctx, const char* key, int64_t value)
     if (!strcmp(key, "scan_taper")) { if (value < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "scan_taper must be >= 1"); ctx->opt_scan_taper = value; return LRC_OK; }
     if (!strcmp(key, "gather_taper")) { if (value < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "gather_taper must be >= 1"); ctx->opt_gather_taper = value; return LRC_OK; }
     if (!strcmp(key, "gather_ramp")) { if (value < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "gather_ramp must be >= 1"); ctx->opt_gather_ramp = value; return LRC_OK; }
+    if (!strcmp(key, "push_tile")) {
+        if (value < 2048 || value > TMA_TILE_MAX || (value & 2047)) return lrc_fail(ctx, LRC_ERR_INVALID, "push_tile must be a multiple of 2048 in [2048, 16384]");
+        ctx->opt_push_tile = value;
+        return LRC_OK;
+    }
     if (!strcmp(key, "push_mode")) { if (value < 0 || value > 1) return lrc_fail(ctx, LRC_ERR_INVALID, "push_mode must be 0 (LSU kernel) or 1 (TMA bulk copies)"); ctx->opt_push_mode = value; return LRC_OK; }
     if (!strcmp(key, "push_blocks")) { if (value < 1 || value > 1024) return lrc_fail(ctx, LRC_ERR_INVALID, "push_blocks must be in [1, 1024]"); ctx->opt_push_blocks = value; return LRC_OK; }
     if (!strcmp(key, "gather_chunks")) { if (value < 1) return lrc_fail(ctx, LRC_ERR_INVALID, "gather_chunks must be >= 1"); ctx->opt_gather_chunks = value; return LRC_OK; }

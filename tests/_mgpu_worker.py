@@ -49,7 +49,10 @@ def main():
     engine.ctx.set_option("gather_chunks", 3)
     # uniform chunks; a short first chunk and few exchange blocks; a short last chunk; both short
     # ... and the same through the TMA exchange kernel (push_mode 1)
-    for ramp, taper, blocks, mode in ((1, 1, 16, 0), (2, 1, 3, 0), (1, 3, 16, 0), (4, 4, 8, 0), (1, 1, 16, 1), (2, 3, 3, 1), (1, 1, 1, 1)):
+    for ramp, taper, blocks, mode in ((1, 1, 16, 0), (2, 1, 3, 0), (1, 3, 16, 0), (4, 4, 8, 0), (1, 1, 16, 1), (2, 3, 3, 1), (1, 1, 1, 1), (1, 1, 7, 2)):
+        if mode == 2:                                  # the TMA kernel with its smallest tile (2 KB per stage)
+            engine.ctx.set_option("push_tile", 2048)
+            mode = 1
         engine.ctx.set_option("push_mode", mode)
         engine.ctx.set_option("gather_ramp", ramp)
         engine.ctx.set_option("gather_taper", taper)
@@ -87,6 +90,7 @@ def main():
     except RuntimeError as e:
         assert "frame_capacity" in str(e), e
     pg.disable()
+    engine.ctx.set_option("push_tile", 16384)
     engine.ctx.set_option("gather_ramp", 1)
     engine.ctx.set_option("gather_taper", 1)
     a, b = ref["frame_offset"][sl.start], ref["frame_offset"][sl.stop]
