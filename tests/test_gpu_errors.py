@@ -56,6 +56,19 @@ def test_status_codes_and_messages(lrc):
         ctx.set_option("variant", 4)
     with pytest.raises(nat.LrcError):
         ctx.set_option("block", 96)
+    for key, bad in (("tune", 3), ("push_tile", 1000), ("push_mode", 2), ("scan_chunks", 0), ("gather_taper", 0)):
+        with pytest.raises(nat.LrcError):
+            ctx.set_option(key, bad)
+    # state inspection: known keys answer, unknown ones fail; incident angles / wire format reject bad arguments
+    assert ctx.stat("node_format") == 2 and ctx.stat("num_sms") > 0 and ctx.stat("mesh_generation") >= 1
+    with pytest.raises(nat.LrcError):
+        ctx.stat("no_such_stat")
+    assert lib.lrc_incident_angles(h, None, None, 1, None, 5, None, None) == -1
+    assert lib.lrc_incident_angles(h, None, None, 0, None, 0, None, None) == 0
+    gw = nat.GatherWire()
+    gw.enabled = 1
+    assert lib.lrc_set_gather_wire(h, C.byref(gw)) == -1 and b"lrc_set_gather first" in lib.lrc_last_error(h)
+    assert lib.lrc_set_gather_wire(h, None) == 0
     # the context is still usable after all those failures
     res = ctx.scan(np.eye(4)[None], intr)
     assert res.num_frames == 1
