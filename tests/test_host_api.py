@@ -97,3 +97,35 @@ def test_synthetic_meshes_are_deterministic_and_sized(lrc):
     assert set(np.unique(sem)) == {0, 1, 2, 7, 8, 10}
     wps = lrc.synthetic.office_waypoints(100)
     assert len(wps) == 100 and all(w.z == 1.0 and w.yaw == 0.0 for w in wps)
+
+
+def test_pinned_result_pool_lends_and_takes_back_buffers(monkeypatch):
+    """The per-frame call hands out pooled page-locked buffers AS numpy arrays (core._PinnedPool / _PinnedLease): a buffer
+    returns to the pool exactly when the last array built on it is dropped, an exhausted pool says so (the caller then copies
+    into ordinary arrays), and arrays stay valid after the pool object itself is gone.  CPU: pinning is patched out."""
+    import gc
+    import torch
+    from lrc_b200 import core
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self, raising=False)
+    pool = core._PinnedPool(64, max_items=2)
+    a = pool.acquire()
+    arr_a = a.array(np.float32, 16)
+    arr_a[:] = np.arange(16, dtype=np.float32)
+    view = arr_a.reshape(4, 4)[1:]                         # a view keeps the lease alive as well
+    del a, arr_a
+    b = pool.acquire()
+    arr_b = b.array(np.float64, 8)
+    arr_b[:] = 7.0
+    del b
+    assert pool.acquire() is None                          # both buffers are on loan
+    assert np.array_equal(view, np.arange(16, dtype=np.float32).reshape(4, 4)[1:]) and np.all(arr_b == 7.0)
+    del view
+    gc.collect()
+    assert len(pool.free) == 1
+    c = pool.acquire()                                     # the returned buffer is lent again, no third allocation
+    assert c is not None and pool.count == 2 and pool.acquire() is None
+    arr_c = c.array(np.float32, 4)
+    del c, pool
+    gc.collect()
+    arr_c[:] = 1.0                                         # still backed by live memory after the pool is gone
+    assert arr_c.flags.writeable and arr_c.sum() == 4.0 and np.all(arr_b == 7.0)
