@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "liblrc.so")
 SOURCES = ["bvh_build.cu", "scan.cu", "post.cu", "plan.cu", "nn.cu"]
-HEADERS = ["common.cuh", "traverse.cuh", "scan_util.cuh", os.path.join("..", "..", "include", "lrc.h")]
+HEADERS = ["common.cuh", "traverse.cuh", "scan_util.cuh", "exchange.cuh", os.path.join("..", "..", "include", "lrc.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
